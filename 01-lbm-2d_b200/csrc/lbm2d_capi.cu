@@ -1,0 +1,481 @@
+// C ABI of the B200-native D2Q9 MRT-LES step (see include/lbm2d.h).  Host side: owns the device
+// buffers, derives the fp32 constants the way the reference's Taichi program does, launches the
+// kernels of lbm2d_kernels.cuh.  No CPU fallback: every path below needs a CUDA device.
+#include "../../include/lbm2d.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lbm2d_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct LbmSolver {
+    LbmParams p{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nx_local = 0, ny = 0, pitch = 0, nseg = 0, n_items = 0;
+    int own0 = 0;  // first owned local column
+    int x_off = 0;
+    bool west_ring = true, east_ring = true;
+    long long plane = 0;
+    float *f[2] = {nullptr, nullptr};
+    uint8_t *code = nullptr;
+    float *damp_x = nullptr, *damp_y = nullptr, *ramp_tab = nullptr;
+    int *ctr = nullptr;
+    float *rho = nullptr, *ux = nullptr, *uy = nullptr;
+    unsigned *maxv = nullptr;
+    lbm::Link *links = nullptr;
+    int n_links = 0;
+    double *force_partial = nullptr;
+    float *force_out = nullptr;
+    float *staging = nullptr;
+    size_t staging_floats = 0;
+    int64_t steps_done = 0;
+    int64_t launches = 0;
+    bool inited = false;
+    lbm::Physics phys{};
+
+    ~LbmSolver() {
+        cudaSetDevice(device);
+        for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
+                          (void *)ctr, (void *)rho, (void *)ux, (void *)uy, (void *)maxv, (void *)links,
+                          (void *)force_partial, (void *)force_out, (void *)staging})
+            if (ptr) cudaFree(ptr);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+constexpr int kForceBlocks = 128;
+
+int ensure_staging(LbmSolver *s, size_t floats) {
+    if (s->staging_floats >= floats) return LBM_OK;
+    if (s->staging) cudaFree(s->staging);
+    s->staging = nullptr;
+    s->staging_floats = 0;
+    CUDA_TRY(cudaMalloc(&s->staging, floats * sizeof(float)));
+    s->staging_floats = floats;
+    return LBM_OK;
+}
+
+// The reference's sponge profile (ref:364-378), evaluated in fp32 exactly as the kernel would.
+float sponge_1d(int i, int n, int w_lo, int w_hi, float strength, bool lo_first) {
+    // x: `if i > n - w_hi ... elif i < w_lo`;  y: `if j < w_lo ... elif j > n - w_hi`
+    auto hi = [&]() { float c = (float)(i - (n - w_hi)) / (float)w_hi; return strength * (c * c); };
+    auto lo = [&]() { float c = (float)(w_lo - i) / (float)w_lo; return strength * (c * c); };
+    if (lo_first) {
+        if (i < w_lo) return lo();
+        if (i > n - w_hi) return hi();
+    } else {
+        if (i > n - w_hi) return hi();
+        if (i < w_lo) return lo();
+    }
+    return 0.0f;
+}
+
+// Cosine soft start (ref:442-443) for frame_count = t; the cosine is the correctly rounded fp32 of
+// the double cosine (see oracle/lbm_oracle_np.py).
+float ramp_at(int t, int warmup) {
+    float progress = (warmup == 0) ? 1.0f : std::fmin(1.0f, (float)t / (float)warmup);
+    const float arg = (float)(0.5 * 3.14159265) * progress;
+    const float c = (float)std::cos((double)arg);
+    return 1.0f - c;
+}
+
+lbm::StepArgs make_args(const LbmSolver *s) {
+    lbm::StepArgs a{};
+    const int par = (int)(s->steps_done & 1);
+    a.src = s->f[par];
+    a.dst = s->f[par ^ 1];
+    a.code = s->code;
+    a.damp_x = s->damp_x;
+    a.damp_y = s->damp_y;
+    a.ramp_tab = s->ramp_tab;
+    a.ctr_in = s->ctr + par;
+    a.ctr_out = s->ctr + (par ^ 1);
+    a.rho = s->rho;
+    a.ux = s->ux;
+    a.uy = s->uy;
+    a.maxv_bits = s->maxv;
+    a.plane = s->plane;
+    a.nx_local = s->nx_local;
+    a.ny = s->ny;
+    a.pitch = s->pitch;
+    a.nseg = s->nseg;
+    a.n_items = s->n_items;
+    a.x_off = s->x_off;
+    a.west_ring = s->west_ring;
+    a.east_ring = s->east_ring;
+    a.warmup = s->p.warmup_steps;
+    a.phys = s->phys;
+    return a;
+}
+
+lbm::ExportArgs make_export_args(const LbmSolver *s) {
+    lbm::ExportArgs a{};
+    const int par = (int)(s->steps_done & 1);
+    a.cur = s->f[par];
+    a.prev = s->f[par ^ 1];
+    a.code = s->code;
+    a.damp_x = s->damp_x;
+    a.damp_y = s->damp_y;
+    a.plane = s->plane;
+    a.nx_local = s->nx_local;
+    a.ny = s->ny;
+    a.pitch = s->pitch;
+    a.il0 = s->own0;
+    a.il1 = s->own0 + s->p.nx;
+    a.x_off = s->x_off;
+    a.nx_global = s->p.nx_global;
+    a.have_prev = s->steps_done > 0;
+    a.strict = s->p.arith == LBM_ARITH_STRICT;
+    a.phys = s->phys;
+    return a;
+}
+
+int check_handle(LbmHandle h, bool need_init) {
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    if (need_init && !h->inited) return fail(LBM_ERR_STATE, "lbm_init() has not been called");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lbm_abi_version(void) { return LBM2D_ABI_VERSION; }
+const char *lbm_last_error(void) { return g_err.c_str(); }
+
+int lbm_device_count(int *count) {
+    if (!count) return fail(LBM_ERR_INVALID, "count is null");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return LBM_OK;
+}
+
+int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) {
+    if (!params || !out) return fail(LBM_ERR_INVALID, "params / out is null");
+    const LbmParams &p = *params;
+    if (p.nx < 1 || p.ny < 3) return fail(LBM_ERR_INVALID, "need nx >= 1 (owned) and ny >= 3");
+    if (p.nx_global < 3) return fail(LBM_ERR_INVALID, "need nx_global >= 3");
+    if (p.slab_x0 < 0 || p.slab_x0 + p.nx > p.nx_global) return fail(LBM_ERR_INVALID, "slab outside the global domain");
+    if (p.warmup_steps < 0) return fail(LBM_ERR_INVALID, "warmup_steps < 0");
+    if (p.obstacle_mode != LBM_OBSTACLE_REFILL) return fail(LBM_ERR_INVALID, "unsupported obstacle_mode");
+    if (p.arith != LBM_ARITH_FAST && p.arith != LBM_ARITH_STRICT) return fail(LBM_ERR_INVALID, "unsupported arith");
+    if (p.warmup_steps > (1 << 26)) return fail(LBM_ERR_INVALID, "warmup_steps too large for the ramp table");
+
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0)
+        return fail(LBM_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e0));
+    int dev = p.device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(LBM_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(dev));
+
+    LbmSolver *s = new (std::nothrow) LbmSolver();
+    if (!s) return fail(LBM_ERR_INVALID, "out of host memory");
+    s->p = p;
+    s->device = dev;
+    const bool west_halo = p.slab_x0 > 0, east_halo = p.slab_x0 + p.nx < p.nx_global;
+    s->west_ring = !west_halo;
+    s->east_ring = !east_halo;
+    s->own0 = west_halo ? 1 : 0;
+    s->x_off = p.slab_x0 - (west_halo ? 1 : 0);
+    s->nx_local = p.nx + (west_halo ? 1 : 0) + (east_halo ? 1 : 0);
+    if (s->nx_local < 3) {
+        delete s;
+        return fail(LBM_ERR_INVALID, "a slab needs at least 3 local columns");
+    }
+    s->ny = p.ny;
+    s->pitch = round_up(p.ny, 32);
+    s->plane = (long long)s->nx_local * s->pitch;
+    s->nseg = (s->pitch + lbm::kSegCells - 1) / lbm::kSegCells;
+    s->n_items = (s->nx_local - 2) * s->nseg;
+
+    // fp32 constants, derived like the reference's Python scope + Taichi f32 casts
+    const double tau0 = 3.0 * p.nu + 0.5;                       // ref:44
+    s->phys.tau0 = (float)tau0;
+    s->phys.tau0_sq = (float)(tau0 * tau0);                     // ref:348 (python-scope power, then f32)
+    s->phys.cs_factor = (float)(18.0 * (p.c_smag * p.c_smag));  // ref:79
+    s->phys.s_ghost = (float)p.s_ghost;
+    s->phys.les_on = p.c_smag > 0.001;                          // ref:342
+    s->phys.rho_in = (float)p.rho_in;
+    s->phys.rho_out = (float)p.rho_out;
+    for (int d = 0; d < 4; ++d) {
+        s->phys.bc_type[d] = p.bc_type[d];
+        s->phys.bc_val[d][0] = p.bc_value[d][0];
+        s->phys.bc_val[d][1] = p.bc_value[d][1];
+    }
+    s->phys.nx_global = p.nx_global;
+
+#define CREATE_TRY(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            delete s;                                                                               \
+            return fail(LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+        }                                                                                           \
+    } while (0)
+
+    CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const size_t fbytes = ((size_t)9 * s->plane + 64) * sizeof(float);  // +64: the last segment may prefetch past the end
+    CREATE_TRY(cudaMalloc(&s->f[0], fbytes));
+    CREATE_TRY(cudaMalloc(&s->f[1], fbytes));
+    CREATE_TRY(cudaMemset(s->f[0], 0, fbytes));
+    CREATE_TRY(cudaMemset(s->f[1], 0, fbytes));
+    CREATE_TRY(cudaMalloc(&s->rho, s->plane * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->ux, s->plane * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->uy, s->plane * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->code, (size_t)s->plane + 64));
+    CREATE_TRY(cudaMalloc(&s->damp_x, s->nx_local * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->damp_y, s->pitch * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->ramp_tab, ((size_t)p.warmup_steps + 1) * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->ctr, 2 * sizeof(int)));
+    CREATE_TRY(cudaMalloc(&s->maxv, 2 * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&s->force_partial, kForceBlocks * 2 * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&s->force_out, 2 * sizeof(float)));
+
+    // cell codes (bit0 = solid), padded to the pitch
+    std::vector<uint8_t> code((size_t)s->plane + 64, 0);
+    if (mask_xy)
+        for (int il = 0; il < s->nx_local; ++il)
+            for (int j = 0; j < s->ny; ++j) code[(size_t)il * s->pitch + j] = mask_xy[(size_t)il * s->ny + j] ? 1 : 0;
+    CREATE_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
+
+    // sponge tables (ref:90-94 widths are max(1, cfg))
+    const int w_in = std::max(1, p.sponge_in), w_out = std::max(1, p.sponge_out);
+    const int w_top = std::max(1, p.sponge_top), w_bot = std::max(1, p.sponge_bot);
+    const float strength = (float)p.sponge_strength;
+    std::vector<float> dx(s->nx_local), dy(s->pitch, 0.0f);
+    for (int il = 0; il < s->nx_local; ++il) dx[il] = sponge_1d(s->x_off + il, p.nx_global, w_in, w_out, strength, false);
+    for (int j = 0; j < s->ny; ++j) dy[j] = sponge_1d(j, s->ny, w_bot, w_top, strength, true);
+    CREATE_TRY(cudaMemcpy(s->damp_x, dx.data(), dx.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(s->damp_y, dy.data(), dy.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    std::vector<float> ramp((size_t)p.warmup_steps + 1);
+    for (int t = 0; t <= p.warmup_steps; ++t) ramp[t] = ramp_at(t, p.warmup_steps);
+    CREATE_TRY(cudaMemcpy(s->ramp_tab, ramp.data(), ramp.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    // solid-fluid links of the momentum-exchange force (ref:597-641), for solids in OWNED columns
+    {
+        static const int inv[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+        static const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+        std::vector<lbm::Link> links;
+        for (int il = s->own0; il < s->own0 + p.nx; ++il)
+            for (int j = 0; j < s->ny; ++j) {
+                if (!code[(size_t)il * s->pitch + j]) continue;
+                for (int k = 1; k < 9; ++k) {
+                    const int nl = il + ex[k], nj = j + ey[k], ng = s->x_off + nl;
+                    if (ng < 0 || ng >= p.nx_global || nj < 0 || nj >= s->ny) continue;
+                    if (code[(size_t)nl * s->pitch + nj]) continue;
+                    const bool ring = ng == 0 || ng == p.nx_global - 1 || nj == 0 || nj == s->ny - 1;
+                    lbm::Link l;
+                    l.offset = (int)((long long)nl * s->pitch + nj);
+                    l.packed = inv[k] | ((int)ring << 4) | ((-ex[k] + 1) << 5) | ((-ey[k] + 1) << 7);
+                    links.push_back(l);
+                }
+            }
+        s->n_links = (int)links.size();
+        if (s->plane > 0x7fffffffLL) {
+            delete s;
+            return fail(LBM_ERR_INVALID, "slab too large for 32-bit link offsets");
+        }
+        if (s->n_links) {
+            CREATE_TRY(cudaMalloc(&s->links, links.size() * sizeof(lbm::Link)));
+            CREATE_TRY(cudaMemcpy(s->links, links.data(), links.size() * sizeof(lbm::Link), cudaMemcpyHostToDevice));
+        }
+    }
+#undef CREATE_TRY
+    *out = s;
+    return LBM_OK;
+}
+
+int lbm_destroy(LbmHandle h) {
+    if (!h) return LBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    delete h;
+    return LBM_OK;
+}
+
+int lbm_init(LbmHandle h) {
+    if (int rc = check_handle(h, false)) return rc;
+    lbm::init_kernel<<<1184, 256, 0, h->stream>>>(h->f[0], h->f[1], h->rho, h->ux, h->uy, h->plane, h->ny, h->pitch);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemsetAsync(h->ctr, 0, 2 * sizeof(int), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
+    h->steps_done = 0;
+    h->inited = true;
+    return LBM_OK;
+}
+
+int lbm_run(LbmHandle h, int steps) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (steps < 0) return fail(LBM_ERR_INVALID, "steps < 0");
+    const bool strict = h->p.arith == LBM_ARITH_STRICT;
+    const int blocks = (h->n_items + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+    for (int it = 0; it < steps; ++it) {
+        const lbm::StepArgs a = make_args(h);
+        const bool emit = (it == steps - 1);
+        if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
+        if (strict) {
+            if (emit) lbm::step_kernel<true, true><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
+            else lbm::step_kernel<true, false><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
+        } else {
+            if (emit) lbm::step_kernel<false, true><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
+            else lbm::step_kernel<false, false><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
+        }
+        h->steps_done++;
+        h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+int lbm_synchronize(LbmHandle h) {
+    if (int rc = check_handle(h, false)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_step_count(LbmHandle h, int64_t *steps) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!steps) return fail(LBM_ERR_INVALID, "steps is null");
+    int v = 0;  // read the device counter: it is what the kernels use for the ramp
+    CUDA_TRY(cudaMemcpyAsync(&v, h->ctr + (h->steps_done & 1), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *steps = v;
+    return LBM_OK;
+}
+
+int lbm_get_force(LbmHandle h, float out_xy[2]) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!out_xy) return fail(LBM_ERR_INVALID, "out is null");
+    out_xy[0] = out_xy[1] = 0.0f;
+    if (h->n_links == 0) return lbm_synchronize(h);
+    const int par = (int)(h->steps_done & 1);
+    lbm::force_kernel<<<kForceBlocks, 256, 0, h->stream>>>(h->f[par], h->plane, h->links, h->n_links, h->force_partial);
+    lbm::force_final_kernel<<<1, 32, 0, h->stream>>>(h->force_partial, kForceBlocks, h->force_out);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(out_xy, h->force_out, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_get_max_velocity(LbmHandle h, float *out) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    unsigned v[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(v, h->maxv, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float m2;
+    std::memcpy(&m2, &v[0], sizeof(float));
+    *out = v[1] ? NAN : std::sqrt(m2);  // max of sqrt == sqrt of max (ref:652-653)
+    return LBM_OK;
+}
+
+static int get_planes(LbmHandle h, const float *p0, const float *p1, int nch, float *out) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    const size_t n = (size_t)h->p.nx * h->ny * nch;
+    if (int rc = ensure_staging(h, n)) return rc;
+    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    lbm::pack_planes_kernel<<<grid, 128, 0, h->stream>>>(p0, p1, nch, h->own0, h->ny, h->pitch, h->staging);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_get_vel(LbmHandle h, float *out) { return h ? get_planes(h, h->ux, h->uy, 2, out) : fail(LBM_ERR_INVALID, "null handle"); }
+int lbm_get_rho(LbmHandle h, float *out) { return h ? get_planes(h, h->rho, nullptr, 1, out) : fail(LBM_ERR_INVALID, "null handle"); }
+
+int lbm_get_mask(LbmHandle h, float *out) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    const size_t n = (size_t)h->p.nx * h->ny;
+    if (int rc = ensure_staging(h, n)) return rc;
+    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    lbm::mask_to_float_kernel<<<grid, 128, 0, h->stream>>>(h->code, h->own0, h->ny, h->pitch, h->staging);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+static int export9(LbmHandle h, int mode, float *out) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    const size_t n = (size_t)h->p.nx * h->ny * 9;
+    if (int rc = ensure_staging(h, n)) return rc;
+    const lbm::ExportArgs a = make_export_args(h);
+    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    lbm::export9_kernel<<<grid, 128, 0, h->stream>>>(a, mode, h->staging);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_get_moments(LbmHandle h, float *out) { return export9(h, 0, out); }
+int lbm_get_f(LbmHandle h, int which, float *out) {
+    if (which != 0 && which != 1) return fail(LBM_ERR_INVALID, "which must be 0 (f_old) or 1 (f_new)");
+    return export9(h, which == 0 ? 1 : 2, out);
+}
+
+int lbm_device_view(LbmHandle h, LbmDeviceView *out) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    const int par = (int)(h->steps_done & 1);
+    out->f_cur = h->f[par];
+    out->f_prev = h->f[par ^ 1];
+    out->rho = h->rho;
+    out->ux = h->ux;
+    out->uy = h->uy;
+    out->cell_code = h->code;
+    out->nx_local = h->nx_local;
+    out->ny = h->ny;
+    out->pitch = h->pitch;
+    out->plane_stride = h->plane;
+    out->stream = (void *)h->stream;
+    return LBM_OK;
+}
+
+int lbm_launch_count(LbmHandle h, int64_t *launches) {
+    if (!h || !launches) return fail(LBM_ERR_INVALID, "null argument");
+    *launches = h->launches;
+    return LBM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+// Kernels of the fused D2Q9 MRT-LES step (sm_100a).  See DESIGN.md for the data layout.
+//
+// Layout in HBM: 9 SoA planes per buffer, each (nx_local, pitch) with y fastest and
+// pitch = round_up(ny, 32) floats, so every column starts on a 128-byte line and a warp's
+// float4 accesses are full, aligned lines.  Two buffers (src/dst) swap roles every step.
+#pragma once
+#include "lbm2d_device.cuh"
+
+namespace lbm {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kCellsPerThread = 4;
+constexpr int kSegCells = 32 * kCellsPerThread;  // cells of one column handled by one warp
+
+struct StepArgs {
+    const float *__restrict__ src;  // 9 planes
+    float *__restrict__ dst;        // 9 planes
+    const uint8_t *__restrict__ code;  // cell code, bit0 = solid
+    const float *__restrict__ damp_x;  // [nx_local]   ref:364-370 (indexed by local column, holds the global value)
+    const float *__restrict__ damp_y;  // [pitch]      ref:372-378
+    const float *__restrict__ ramp_tab;  // [warmup+1]  ref:442-443
+    const int *ctr_in;              // frame_count before this step
+    int *ctr_out;                   // frame_count after this step (other parity slot)
+    float *rho, *ux, *uy;           // macroscopic planes (written by EMIT steps)
+    unsigned *maxv_bits;            // max(ux^2+uy^2) as ordered uint; [1] = NaN flag
+    long long plane;                // floats per plane = nx_local * pitch
+    int nx_local, ny, pitch, nseg, n_items;
+    int x_off;                      // global x of local column 0
+    int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
+    int warmup;
+    Physics phys;
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+
+// Scalar write-out of one ring cell (O(perimeter) work): f, and on EMIT steps rho / u.
+template <bool EMIT>
+__device__ __forceinline__ void store_cell(const StepArgs &a, int il, int j, const Cell &c) {
+    const long long o = (long long)il * a.pitch + j;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.dst[k * a.plane + o] = c.f[k];
+    if (EMIT) {
+        a.rho[o] = c.rho;
+        a.ux[o] = c.ux;
+        a.uy[o] = c.uy;
+    }
+}
+
+__device__ __forceinline__ float vmag2_strict(float ux, float uy) {
+    return __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy));
+}
+
+// One fused pass: pull-stream, MRT-LES collision, sponge, macroscopic update, boundary ring,
+// obstacle refill (ref:552-573 = collide_and_stream + update_macro_var + apply_bc), f_src -> f_dst.
+//
+// Work decomposition: one warp = one 128-cell segment of one interior column; one thread = 4
+// consecutive cells in y (128-bit accesses).  The +-1 shift of the pull in y comes from the
+// neighbouring lane by warp shuffle, with one extra scalar load at each end of the segment.
+// Ring cells are produced by the thread that owns their interior neighbour.
+template <bool STRICT, bool EMIT>
+__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
+    if (item >= a.n_items) return;                                          // warp-uniform
+    const int il = 1 + item / a.nseg;                                        // local column
+    const int j0 = (item % a.nseg) * kSegCells + lane * kCellsPerThread;
+    const bool lane_on = j0 < a.pitch;
+    const int ny = a.ny, pitch = a.pitch;
+    const long long plane = a.plane;
+
+    // ---- pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky) -----------------------
+    float fin[kCellsPerThread][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float *col = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane_on) v = ldg4(col + j0);
+        if (kEy[k] == 0) {
+            fin[0][k] = v.x; fin[1][k] = v.y; fin[2][k] = v.z; fin[3][k] = v.w;
+        } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
+            float below = __shfl_up_sync(0xffffffffu, v.w, 1);
+            if (lane == 0 && lane_on && j0 > 0) below = __ldg(col + j0 - 1);
+            fin[0][k] = below; fin[1][k] = v.x; fin[2][k] = v.y; fin[3][k] = v.z;
+        } else {                   // needs j+1: first element of the lane above
+            float above = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31 && j0 + 4 < ny) above = __ldg(col + j0 + 4);
+            fin[0][k] = v.y; fin[1][k] = v.z; fin[2][k] = v.w; fin[3][k] = above;
+        }
+    }
+    // Padding lanes (j0 >= ny) only fed the shuffles; they stay in the warp for the EMIT reduction.
+    const bool live = lane_on && j0 < ny;
+    float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
+    bool vnan = false;
+    if (live) {
+    const float dx = __ldg(a.damp_x + il);
+    const float4 dy4 = ldg4(a.damp_y + j0);
+    const float dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+    const uchar4 code4 = __ldg(reinterpret_cast<const uchar4 *>(a.code + (long long)il * pitch + j0));
+    const unsigned char code[4] = {code4.x, code4.y, code4.z, code4.w};
+
+    // ---- collide + macro (ref:266-436) ------------------------------------------------------
+    float g[kCellsPerThread][9];
+    float rho[kCellsPerThread], ux[kCellsPerThread], uy[kCellsPerThread];
+#pragma unroll
+    for (int c = 0; c < kCellsPerThread; ++c) {
+        const float damp = fmaxf(dx, dy[c]);
+        if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
+        else collide_fast(a.phys, fin[c], damp, g[c]);
+        macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+    }
+
+    // ---- boundary ring (ref:438-450), produced from the owners' fresh pre-refill state -------
+    const bool first_col = (il == 1) && a.west_ring;
+    const bool last_col = (il == a.nx_local - 2) && a.east_ring;
+    const int ig = a.x_off + il;  // global x of this column
+    float ramp = 0.0f;
+    const bool touches_ring = (j0 == 0) || (j0 + kCellsPerThread >= ny - 1) || first_col || last_col;
+    if (touches_ring) {
+        const int fc = *a.ctr_in + 1;
+        ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
+    }
+    if (touches_ring) {
+#pragma unroll
+        for (int c = 0; c < kCellsPerThread; ++c) {
+            const int j = j0 + c;
+            if (j < 1 || j > ny - 2) continue;
+            const bool bottom = (j == 1), top = (j == ny - 2);
+            if (!(bottom || top || first_col || last_col)) continue;
+            Cell me;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) me.f[k] = g[c][k];
+            me.rho = rho[c]; me.ux = ux[c]; me.uy = uy[c];
+            // W / E columns first (ref:445-447), then rows incl. corners (ref:448-450)
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const bool on = side == 0 ? first_col : last_col;
+                if (!on) continue;
+                const int ilr = side == 0 ? 0 : a.nx_local - 1;
+                const int igr = side == 0 ? ig - 1 : ig + 1;
+                Cell r;
+                cell_rest(r);
+                bc_core(a.phys, side == 0 ? 0 : 2, igr, ig, me, r, ramp);
+                // corners chain through the W/E cell just produced, un-refilled
+                if (top) {
+                    Cell cr;
+                    cell_rest(cr);
+                    bc_core(a.phys, 1, igr, igr, r, cr, ramp);
+                    if (a.code[(long long)ilr * pitch + ny - 1] & 1) refill(cr);
+                    store_cell<EMIT>(a, ilr, ny - 1, cr);
+                    if (EMIT) { const float m2 = vmag2_strict(cr.ux, cr.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
+                }
+                if (bottom) {
+                    Cell cr;
+                    cell_rest(cr);
+                    bc_core(a.phys, 3, igr, igr, r, cr, ramp);
+                    if (a.code[(long long)ilr * pitch] & 1) refill(cr);
+                    store_cell<EMIT>(a, ilr, 0, cr);
+                    if (EMIT) { const float m2 = vmag2_strict(cr.ux, cr.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
+                }
+                if (a.code[(long long)ilr * pitch + j] & 1) refill(r);
+                store_cell<EMIT>(a, ilr, j, r);
+                if (EMIT) { const float m2 = vmag2_strict(r.ux, r.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
+            }
+            if (top) {
+                Cell r;
+                cell_rest(r);
+                bc_core(a.phys, 1, ig, ig, me, r, ramp);
+                if (a.code[(long long)il * pitch + ny - 1] & 1) refill(r);
+                if (c < kCellsPerThread - 1) {  // ring cell lies in this thread's float4: merge
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) g[(c + 1) & 3][k] = r.f[k];
+                    rho[(c + 1) & 3] = r.rho; ux[(c + 1) & 3] = r.ux; uy[(c + 1) & 3] = r.uy;
+                } else {
+                    store_cell<EMIT>(a, il, ny - 1, r);
+                    if (EMIT) { const float m2 = vmag2_strict(r.ux, r.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
+                }
+            }
+            if (bottom) {  // j == 1 is always cell 1 of the first float4; the ring cell is cell 0
+                Cell r;
+                cell_rest(r);
+                bc_core(a.phys, 3, ig, ig, me, r, ramp);
+                if (a.code[(long long)il * pitch] & 1) refill(r);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) g[0][k] = r.f[k];
+                rho[0] = r.rho; ux[0] = r.ux; uy[0] = r.uy;
+            }
+        }
+    }
+
+    // ---- obstacle refill of interior cells (ref:452-455) and write-out ------------------------
+    // Cells of this float4: interior (refill by code), ring cells merged above (already final),
+    // padding j >= ny (zeros).  A float4 that starts on the top ring cell itself (ny-1 == j0) has
+    // no interior cell: its ring value is written by the owner of j = ny-2, so skip the store.
+    if (j0 != ny - 1) {
+#pragma unroll
+    for (int c = 0; c < kCellsPerThread; ++c) {
+        const int j = j0 + c;
+        const bool interior = (j >= 1) && (j <= ny - 2);
+        if (interior && (code[c] & 1)) {
+            ux[c] = 0.0f; uy[c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+        }
+        if (j >= ny) {
+            rho[c] = 0.0f; ux[c] = 0.0f; uy[c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[c][k] = 0.0f;
+        }
+    }
+    const long long o = (long long)il * pitch + j0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st4(a.dst + k * plane + o, g[0][k], g[1][k], g[2][k], g[3][k]);
+
+    if (EMIT) {
+        st4(a.rho + o, rho[0], rho[1], rho[2], rho[3]);
+        st4(a.ux + o, ux[0], ux[1], ux[2], ux[3]);
+        st4(a.uy + o, uy[0], uy[1], uy[2], uy[3]);
+#pragma unroll
+        for (int c = 0; c < kCellsPerThread; ++c) {
+            const float m2 = vmag2_strict(ux[c], uy[c]);
+            vnan |= (m2 != m2);
+            vmax = fmaxf(vmax, m2);
+        }
+    }
+    }  // j0 != ny - 1
+    }  // live
+
+    if (EMIT) {  // whole warp: max over lanes, one atomic per warp and only if it raises the running max
+        for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+        const bool any_nan = __any_sync(0xffffffffu, vnan);
+        if (lane == 0) {
+            const unsigned bits = __float_as_uint(vmax);
+            if (bits > *a.maxv_bits) atomicMax(a.maxv_bits, bits);
+            if (any_nan) a.maxv_bits[1] = 1u;
+        }
+    }
+}
+
+// init(), ref:235-241: both buffers = w_k, rho = 1, u = 0; padding cells = 0.
+__global__ void init_kernel(float *f0, float *f1, float *rho, float *ux, float *uy, long long plane, int ny, int pitch) {
+    const long long n = plane;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+        const bool real = (int)(o % pitch) < ny;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float v = real ? kW[k] : 0.0f;
+            f0[k * plane + o] = v;
+            f1[k * plane + o] = v;
+        }
+        rho[o] = real ? 1.0f : 0.0f;
+        ux[o] = 0.0f;
+        uy[o] = 0.0f;
+    }
+}
+
+// ---- export / parity kernels (not on the per-step path) ---------------------------------------
+struct ExportArgs {
+    const float *cur;   // state after the last step (= the reference's f_old)
+    const float *prev;  // state before the last step (still intact in the other buffer)
+    const uint8_t *code;
+    const float *damp_x, *damp_y;
+    long long plane;
+    int nx_local, ny, pitch;
+    int il0, il1;       // local columns to export [il0, il1)
+    int x_off, nx_global;
+    int have_prev;      // 0 right after init(): f_new == f_old == w everywhere
+    int strict;
+    Physics phys;
+};
+
+// The reference's f_new (ref:104): post-collision values at interior cells -- equal to `cur` on fluid
+// cells, re-derived from `prev` on solid cells (cur holds their refill there) -- and the initial
+// equilibrium on the boundary ring, which the reference never updates in f_new.
+__device__ __forceinline__ void load_f_new(const ExportArgs &a, int il, int j, float (&f)[9]) {
+    const int ig = a.x_off + il;
+    const bool ring = (ig == 0) || (ig == a.nx_global - 1) || (j == 0) || (j == a.ny - 1);
+    const long long o = (long long)il * a.pitch + j;
+    if (ring) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = kW[k];
+    } else if (!a.have_prev || !(a.code[o] & 1)) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = a.cur[k * a.plane + o];
+    } else {
+        float fin[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) fin[k] = a.prev[k * a.plane + (long long)(il - kEx[k]) * a.pitch + (j - kEy[k])];
+        const float damp = fmaxf(a.damp_x[il], a.damp_y[j]);
+        if (a.strict) collide_strict(a.phys, fin, damp, f);
+        else collide_fast(a.phys, fin, damp, f);
+    }
+}
+
+// mode 0: moments of f_new (ref:667-737);  1: f_old as AoS;  2: f_new as AoS.   out: (ncols, ny, 9)
+__global__ void export9_kernel(const ExportArgs a, int mode, float *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int il = a.il0 + blockIdx.y;
+    if (j >= a.ny) return;
+    float f[9], o9[9];
+    if (mode == 1) {
+        const long long o = (long long)il * a.pitch + j;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o9[k] = a.cur[k * a.plane + o];
+    } else {
+        load_f_new(a, il, j, f);
+        if (mode == 0) moments_strict(f, o9);
+        else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) o9[k] = f[k];
+        }
+    }
+    float *dst = out + ((long long)(il - a.il0) * a.ny + j) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dst[k] = o9[k];
+}
+
+// (ncols, ny, nch) interleaved from up to 2 pitched planes (vel: ux,uy; rho: one plane).
+__global__ void pack_planes_kernel(const float *p0, const float *p1, int nch, int il0, int ny, int pitch, float *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int il = il0 + blockIdx.y;
+    if (j >= ny) return;
+    const long long o = (long long)il * pitch + j;
+    float *dst = out + ((long long)blockIdx.y * ny + j) * nch;
+    dst[0] = p0[o];
+    if (nch == 2) dst[1] = p1[o];
+}
+
+__global__ void mask_to_float_kernel(const uint8_t *code, int il0, int ny, int pitch, float *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int il = il0 + blockIdx.y;
+    if (j >= ny) return;
+    out[(long long)blockIdx.y * ny + j] = (code[(long long)il * pitch + j] & 1) ? 1.0f : 0.0f;
+}
+
+// Momentum exchange over the precomputed solid-fluid links, ref:588-641.
+// link = (offset of the fluid neighbour in a plane) , packed (inv_k | ring<<4 | (fx+1)<<5 | (fy+1)<<7)
+struct Link {
+    int offset;
+    int packed;
+};
+__global__ void force_kernel(const float *cur, long long plane, const Link *links, int n_links, double *partial /*[grid][2]*/) {
+    double fx = 0.0, fy = 0.0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_links; t += gridDim.x * blockDim.x) {
+        const Link l = links[t];
+        const int inv_k = l.packed & 15;
+        const bool ring = (l.packed >> 4) & 1;
+        const int sx = ((l.packed >> 5) & 3) - 1, sy = ((l.packed >> 7) & 3) - 1;
+        const float fv = 2.0f * (ring ? kW[inv_k] : cur[inv_k * plane + l.offset]);  // ring: f_new keeps its init value
+        fx += (double)(fv * (float)sx);
+        fy += (double)(fv * (float)sy);
+    }
+    __shared__ double sx_[32], sy_[32];
+    for (int s = 16; s > 0; s >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, s);
+        fy += __shfl_xor_sync(0xffffffffu, fy, s);
+    }
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sx_[w] = fx; sy_[w] = fy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ax = 0.0, ay = 0.0;
+        for (int i = 0; i < nw; ++i) { ax += sx_[i]; ay += sy_[i]; }
+        partial[blockIdx.x * 2] = ax;
+        partial[blockIdx.x * 2 + 1] = ay;
+    }
+}
+__global__ void force_final_kernel(const double *partial, int n, float *out2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double ax = 0.0, ay = 0.0;
+        for (int i = 0; i < n; ++i) { ax += partial[2 * i]; ay += partial[2 * i + 1]; }
+        out2[0] = (float)ax;
+        out2[1] = (float)ay;
+    }
+}
+
+}  // namespace lbm
