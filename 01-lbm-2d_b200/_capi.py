@@ -16,7 +16,7 @@ class LbmParams(C.Structure):
         ("sponge_in", C.c_int32), ("sponge_out", C.c_int32), ("sponge_top", C.c_int32), ("sponge_bot", C.c_int32),
         ("sponge_strength", C.c_double),
         ("bc_type", C.c_int32 * 4), ("bc_value", (C.c_float * 2) * 4),
-        ("arith", C.c_int32), ("obstacle_mode", C.c_int32), ("device", C.c_int32),
+        ("arith", C.c_int32), ("obstacle_mode", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32),
         ("nx_global", C.c_int32), ("slab_x0", C.c_int32),
     ]
 
@@ -30,6 +30,7 @@ class LbmDeviceView(C.Structure):
 
 
 ARITH = {"fast": 0, "strict": 1}
+KERNEL = {"auto": 0, "register": 1, "tma": 2}
 EXPORTS = {
     "lbm_abi_version": (C.c_int, []),
     "lbm_last_error": (C.c_char_p, []),

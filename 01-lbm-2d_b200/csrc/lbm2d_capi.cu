@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "lbm2d_kernels.cuh"
+#include "lbm2d_tma.cuh"
 
 namespace {
 
@@ -45,8 +45,14 @@ struct LbmSolver {
     uint8_t *code = nullptr;
     float *damp_x = nullptr, *damp_y = nullptr, *ramp_tab = nullptr;
     int *ctr = nullptr;
+    float *mac = nullptr;  // rho | ux | uy, three consecutive planes (one TMA store tensor)
     float *rho = nullptr, *ux = nullptr, *uy = nullptr;
     unsigned *maxv = nullptr;
+    lbm::RingCtx *ring_ctx = nullptr;  // [2], one per destination buffer
+    bool use_tma = false;
+    int tma_grid = 0;
+    CUtensorMap map_src[2], map_dst[2], map_code, map_mac;
+    lbm::TmaArgs tma_args{};
     lbm::Link *links = nullptr;
     int n_links = 0;
     double *force_partial = nullptr;
@@ -61,7 +67,7 @@ struct LbmSolver {
     ~LbmSolver() {
         cudaSetDevice(device);
         for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
-                          (void *)ctr, (void *)rho, (void *)ux, (void *)uy, (void *)maxv, (void *)links,
+                          (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging})
             if (ptr) cudaFree(ptr);
         if (stream) cudaStreamDestroy(stream);
@@ -131,8 +137,87 @@ lbm::StepArgs make_args(const LbmSolver *s) {
     a.west_ring = s->west_ring;
     a.east_ring = s->east_ring;
     a.warmup = s->p.warmup_steps;
+    a.ring = s->ring_ctx + (par ^ 1);
     a.phys = s->phys;
     return a;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(CUtensorMap *map, CUtensorMapDataType dt, int rank, void *base, const cuuint64_t *dims,
+               const cuuint64_t *strides_bytes, const cuuint32_t *box) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !sym)
+            return fail(LBM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        fn = (EncodeTiledFn)sym;
+    }
+    const cuuint32_t ones[3] = {1, 1, 1};
+    CUresult r = fn(map, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LBM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return LBM_OK;
+}
+
+// Tensor maps + static arguments of the TMA variant (see lbm2d_tma.cuh).
+int setup_tma(LbmSolver *s) {
+    using namespace lbm;
+    const int west_halo = s->west_ring ? 0 : 1, east_halo = s->east_ring ? 0 : 1;
+    int col_lo = west_halo, col_hi = s->nx_local - east_halo, row_hi = s->ny;
+    // a ring row / column that would start a tile of its own is written by its owners with scalar stores
+    if ((s->ny - 1) % kTileBY == 0) row_hi = s->ny - 1;
+    if (s->east_ring && (s->nx_local - 1 - col_lo) % kTileBX == 0) col_hi = s->nx_local - 1;
+    TmaArgs &a = s->tma_args;
+    a.damp_x = s->damp_x;
+    a.damp_y = s->damp_y;
+    a.ramp_tab = s->ramp_tab;
+    a.maxv_bits = s->maxv;
+    a.nx_local = s->nx_local;
+    a.ny = s->ny;
+    a.pitch = s->pitch;
+    a.col_lo = col_lo;
+    a.col_hi = col_hi;
+    a.row_hi = row_hi;
+    a.n_tx = (col_hi - col_lo + kTileBX - 1) / kTileBX;
+    a.n_ty = (row_hi + kTileBY - 1) / kTileBY;
+    a.n_tiles = a.n_tx * a.n_ty;
+    a.west_ring = s->west_ring;
+    a.east_ring = s->east_ring;
+    a.warmup = s->p.warmup_steps;
+    a.phys = s->phys;
+
+    const cuuint64_t pitch_b = (cuuint64_t)s->pitch * 4, plane_b = (cuuint64_t)s->plane * 4;
+    const cuuint32_t box3[3] = {(cuuint32_t)kTileBY, (cuuint32_t)kTileBX, 1};
+    for (int b = 0; b < 2; ++b) {
+        const cuuint64_t dsrc[3] = {(cuuint64_t)s->pitch, (cuuint64_t)s->nx_local, 9};
+        const cuuint64_t st[2] = {pitch_b, plane_b};
+        if (int rc = encode_map(&s->map_src[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b], dsrc, st, box3)) return rc;
+        const cuuint64_t ddst[3] = {(cuuint64_t)row_hi, (cuuint64_t)(col_hi - col_lo), 9};
+        if (int rc = encode_map(&s->map_dst[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b] + (size_t)col_lo * s->pitch, ddst, st, box3))
+            return rc;
+    }
+    {
+        const cuuint64_t d[3] = {(cuuint64_t)row_hi, (cuuint64_t)(col_hi - col_lo), 3};
+        const cuuint64_t st[2] = {pitch_b, plane_b};
+        if (int rc = encode_map(&s->map_mac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->mac + (size_t)col_lo * s->pitch, d, st, box3)) return rc;
+        const cuuint64_t dc[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->nx_local};
+        const cuuint64_t stc[1] = {(cuuint64_t)s->pitch};
+        const cuuint32_t box2[2] = {(cuuint32_t)kTileBY, (cuuint32_t)kTileBX};
+        if (int rc = encode_map(&s->map_code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->code, dc, stc, box2)) return rc;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    s->tma_grid = std::min(a.n_tiles, sms);
+    for (auto fnp : {(const void *)step_tma_kernel<false, false>, (const void *)step_tma_kernel<false, true>,
+                     (const void *)step_tma_kernel<true, false>, (const void *)step_tma_kernel<true, true>})
+        CUDA_TRY(cudaFuncSetAttribute(fnp, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+    return LBM_OK;
 }
 
 lbm::ExportArgs make_export_args(const LbmSolver *s) {
@@ -249,9 +334,11 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     CREATE_TRY(cudaMalloc(&s->f[1], fbytes));
     CREATE_TRY(cudaMemset(s->f[0], 0, fbytes));
     CREATE_TRY(cudaMemset(s->f[1], 0, fbytes));
-    CREATE_TRY(cudaMalloc(&s->rho, s->plane * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&s->ux, s->plane * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&s->uy, s->plane * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&s->mac, (size_t)3 * s->plane * sizeof(float)));
+    s->rho = s->mac;
+    s->ux = s->mac + s->plane;
+    s->uy = s->mac + 2 * s->plane;
+    CREATE_TRY(cudaMalloc(&s->ring_ctx, 2 * sizeof(lbm::RingCtx)));
     CREATE_TRY(cudaMalloc(&s->code, (size_t)s->plane + 64));
     CREATE_TRY(cudaMalloc(&s->damp_x, s->nx_local * sizeof(float)));
     CREATE_TRY(cudaMalloc(&s->damp_y, s->pitch * sizeof(float)));
@@ -311,7 +398,42 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
             CREATE_TRY(cudaMemcpy(s->links, links.data(), links.size() * sizeof(lbm::Link), cudaMemcpyHostToDevice));
         }
     }
+    {
+        lbm::RingCtx rc[2];
+        for (int b = 0; b < 2; ++b) {
+            rc[b].phys = s->phys;
+            rc[b].dst = s->f[b];
+            rc[b].rho = s->rho;
+            rc[b].ux = s->ux;
+            rc[b].uy = s->uy;
+            rc[b].code = s->code;
+            rc[b].plane = s->plane;
+            rc[b].nx_local = s->nx_local;
+            rc[b].ny = s->ny;
+            rc[b].pitch = s->pitch;
+            rc[b].x_off = s->x_off;
+            rc[b].west_ring = s->west_ring;
+            rc[b].east_ring = s->east_ring;
+        }
+        CREATE_TRY(cudaMemcpy(s->ring_ctx, rc, sizeof(rc), cudaMemcpyHostToDevice));
+    }
 #undef CREATE_TRY
+    // kernel variant: the persistent TMA pipeline needs enough tiles to occupy every SM
+    {
+        const long long tiles = ((long long)s->nx_local + lbm::kTileBX - 1) / lbm::kTileBX * ((s->ny + lbm::kTileBY - 1) / lbm::kTileBY);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        s->use_tma = p.kernel == LBM_KERNEL_TMA || (p.kernel == LBM_KERNEL_AUTO && tiles >= 4LL * sms);
+        if (p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER && p.kernel != LBM_KERNEL_TMA) {
+            delete s;
+            return fail(LBM_ERR_INVALID, "unsupported kernel variant");
+        }
+        if (s->use_tma)
+            if (int rc = setup_tma(s)) {
+                delete s;
+                return rc;
+            }
+    }
     *out = s;
     return LBM_OK;
 }
@@ -342,9 +464,29 @@ int lbm_run(LbmHandle h, int steps) {
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
     const int blocks = (h->n_items + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
     for (int it = 0; it < steps; ++it) {
-        const lbm::StepArgs a = make_args(h);
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
+        if (h->use_tma) {
+            const int par = (int)(h->steps_done & 1);
+            lbm::TmaArgs ta = h->tma_args;
+            ta.ctr_in = h->ctr + par;
+            ta.ctr_out = h->ctr + (par ^ 1);
+            ta.ring = h->ring_ctx + (par ^ 1);
+            const CUtensorMap &ms = h->map_src[par], &md = h->map_dst[par ^ 1];
+            const dim3 grid(h->tma_grid), block(lbm::kTmaThreads);
+            const size_t sm = lbm::kTmaSmemBytes;
+            if (strict) {
+                if (emit) lbm::step_tma_kernel<true, true><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+                else lbm::step_tma_kernel<true, false><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+            } else {
+                if (emit) lbm::step_tma_kernel<false, true><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+                else lbm::step_tma_kernel<false, false><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+            }
+            h->steps_done++;
+            h->launches++;
+            continue;
+        }
+        const lbm::StepArgs a = make_args(h);
         if (strict) {
             if (emit) lbm::step_kernel<true, true><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
             else lbm::step_kernel<true, false><<<blocks, lbm::kThreads, 0, h->stream>>>(a);

@@ -29,25 +29,13 @@ struct StepArgs {
     int x_off;                      // global x of local column 0
     int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
     int warmup;
+    const RingCtx *ring;            // rare-path context in global memory (dst-specific)
     Physics phys;
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
-}
-
-// Scalar write-out of one ring cell (O(perimeter) work): f, and on EMIT steps rho / u.
-template <bool EMIT>
-__device__ __forceinline__ void store_cell(const StepArgs &a, int il, int j, const Cell &c) {
-    const long long o = (long long)il * a.pitch + j;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a.dst[k * a.plane + o] = c.f[k];
-    if (EMIT) {
-        a.rho[o] = c.rho;
-        a.ux[o] = c.ux;
-        a.uy[o] = c.uy;
-    }
 }
 
 __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
@@ -57,10 +45,11 @@ __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
 // One fused pass: pull-stream, MRT-LES collision, sponge, macroscopic update, boundary ring,
 // obstacle refill (ref:552-573 = collide_and_stream + update_macro_var + apply_bc), f_src -> f_dst.
 //
-// Work decomposition: one warp = one 128-cell segment of one interior column; one thread = 4
-// consecutive cells in y (128-bit accesses).  The +-1 shift of the pull in y comes from the
-// neighbouring lane by warp shuffle, with one extra scalar load at each end of the segment.
-// Ring cells are produced by the thread that owns their interior neighbour.
+// "Register" variant.  Work decomposition: one warp = one 128-cell segment of one interior column;
+// one thread = 4 consecutive cells in y (128-bit accesses).  The +-1 shift of the pull in y comes
+// from the neighbouring lane by warp shuffle, with one extra scalar load at each end of the
+// segment (issued up front with the vector loads).  Ring cells are produced by the thread that owns
+// their interior neighbour (ring_from_owner) and written with scalar stores after the float4 stores.
 template <bool STRICT, bool EMIT>
 __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
     const int lane = threadIdx.x & 31;
@@ -74,165 +63,128 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
     const long long plane = a.plane;
 
     // ---- pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky) -----------------------
-    float fin[kCellsPerThread][9];
+    // phase 1: every load of this thread is issued before the first use
+    float4 v[9];
+    float edge[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const float *col = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane_on) v = ldg4(col + j0);
-        if (kEy[k] == 0) {
-            fin[0][k] = v.x; fin[1][k] = v.y; fin[2][k] = v.z; fin[3][k] = v.w;
-        } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
-            float below = __shfl_up_sync(0xffffffffu, v.w, 1);
-            if (lane == 0 && lane_on && j0 > 0) below = __ldg(col + j0 - 1);
-            fin[0][k] = below; fin[1][k] = v.x; fin[2][k] = v.y; fin[3][k] = v.z;
-        } else {                   // needs j+1: first element of the lane above
-            float above = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31 && j0 + 4 < ny) above = __ldg(col + j0 + 4);
-            fin[0][k] = v.y; fin[1][k] = v.z; fin[2][k] = v.w; fin[3][k] = above;
-        }
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        edge[k] = 0.f;
+        if (lane_on) v[k] = ldg4(col + j0);
+        if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = __ldg(col + j0 - 1);
+        if (kEy[k] == -1 && lane == 31 && j0 + 4 < ny) edge[k] = __ldg(col + j0 + 4);
     }
-    // Padding lanes (j0 >= ny) only fed the shuffles; they stay in the warp for the EMIT reduction.
-    const bool live = lane_on && j0 < ny;
-    float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
-    bool vnan = false;
+    const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
+    float dx = 0.f;
+    float4 dy4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 code4 = make_uchar4(0, 0, 0, 0);
     if (live) {
-    const float dx = __ldg(a.damp_x + il);
-    const float4 dy4 = ldg4(a.damp_y + j0);
-    const float dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
-    const uchar4 code4 = __ldg(reinterpret_cast<const uchar4 *>(a.code + (long long)il * pitch + j0));
-    const unsigned char code[4] = {code4.x, code4.y, code4.z, code4.w};
-
-    // ---- collide + macro (ref:266-436) ------------------------------------------------------
-    float g[kCellsPerThread][9];
-    float rho[kCellsPerThread], ux[kCellsPerThread], uy[kCellsPerThread];
+        dx = __ldg(a.damp_x + il);
+        dy4 = ldg4(a.damp_y + j0);
+        code4 = __ldg(reinterpret_cast<const uchar4 *>(a.code + (long long)il * pitch + j0));
+    }
+    // phase 2: assemble the shifted rows
+    float fin[kCellsPerThread][9];
 #pragma unroll
-    for (int c = 0; c < kCellsPerThread; ++c) {
-        const float damp = fmaxf(dx, dy[c]);
-        if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
-        else collide_fast(a.phys, fin[c], damp, g[c]);
-        macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+    for (int k = 0; k < 9; ++k) {
+        if (kEy[k] == 0) {
+            fin[0][k] = v[k].x; fin[1][k] = v[k].y; fin[2][k] = v[k].z; fin[3][k] = v[k].w;
+        } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
+            float below = __shfl_up_sync(0xffffffffu, v[k].w, 1);
+            if (lane == 0) below = edge[k];
+            fin[0][k] = below; fin[1][k] = v[k].x; fin[2][k] = v[k].y; fin[3][k] = v[k].z;
+        } else {                   // needs j+1: first element of the lane above
+            float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
+            if (lane == 31) above = edge[k];
+            fin[0][k] = v[k].y; fin[1][k] = v[k].z; fin[2][k] = v[k].w; fin[3][k] = above;
+        }
     }
+    float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
+    int vnan = 0;
+    if (live) {
+        const float dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+        const unsigned char code[4] = {code4.x, code4.y, code4.z, code4.w};
 
-    // ---- boundary ring (ref:438-450), produced from the owners' fresh pre-refill state -------
-    const bool first_col = (il == 1) && a.west_ring;
-    const bool last_col = (il == a.nx_local - 2) && a.east_ring;
-    const int ig = a.x_off + il;  // global x of this column
-    float ramp = 0.0f;
-    const bool touches_ring = (j0 == 0) || (j0 + kCellsPerThread >= ny - 1) || first_col || last_col;
-    if (touches_ring) {
-        const int fc = *a.ctr_in + 1;
-        ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
-    }
-    if (touches_ring) {
+        // ---- collide + macro (ref:266-436) --------------------------------------------------
+        float g[kCellsPerThread][9];
+        float rho[kCellsPerThread], ux[kCellsPerThread], uy[kCellsPerThread];
 #pragma unroll
         for (int c = 0; c < kCellsPerThread; ++c) {
-            const int j = j0 + c;
-            if (j < 1 || j > ny - 2) continue;
-            const bool bottom = (j == 1), top = (j == ny - 2);
-            if (!(bottom || top || first_col || last_col)) continue;
-            Cell me;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) me.f[k] = g[c][k];
-            me.rho = rho[c]; me.ux = ux[c]; me.uy = uy[c];
-            // W / E columns first (ref:445-447), then rows incl. corners (ref:448-450)
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const bool on = side == 0 ? first_col : last_col;
-                if (!on) continue;
-                const int ilr = side == 0 ? 0 : a.nx_local - 1;
-                const int igr = side == 0 ? ig - 1 : ig + 1;
-                Cell r;
-                cell_rest(r);
-                bc_core(a.phys, side == 0 ? 0 : 2, igr, ig, me, r, ramp);
-                // corners chain through the W/E cell just produced, un-refilled
-                if (top) {
-                    Cell cr;
-                    cell_rest(cr);
-                    bc_core(a.phys, 1, igr, igr, r, cr, ramp);
-                    if (a.code[(long long)ilr * pitch + ny - 1] & 1) refill(cr);
-                    store_cell<EMIT>(a, ilr, ny - 1, cr);
-                    if (EMIT) { const float m2 = vmag2_strict(cr.ux, cr.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
-                }
-                if (bottom) {
-                    Cell cr;
-                    cell_rest(cr);
-                    bc_core(a.phys, 3, igr, igr, r, cr, ramp);
-                    if (a.code[(long long)ilr * pitch] & 1) refill(cr);
-                    store_cell<EMIT>(a, ilr, 0, cr);
-                    if (EMIT) { const float m2 = vmag2_strict(cr.ux, cr.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
-                }
-                if (a.code[(long long)ilr * pitch + j] & 1) refill(r);
-                store_cell<EMIT>(a, ilr, j, r);
-                if (EMIT) { const float m2 = vmag2_strict(r.ux, r.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
-            }
-            if (top) {
-                Cell r;
-                cell_rest(r);
-                bc_core(a.phys, 1, ig, ig, me, r, ramp);
-                if (a.code[(long long)il * pitch + ny - 1] & 1) refill(r);
-                if (c < kCellsPerThread - 1) {  // ring cell lies in this thread's float4: merge
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) g[(c + 1) & 3][k] = r.f[k];
-                    rho[(c + 1) & 3] = r.rho; ux[(c + 1) & 3] = r.ux; uy[(c + 1) & 3] = r.uy;
-                } else {
-                    store_cell<EMIT>(a, il, ny - 1, r);
-                    if (EMIT) { const float m2 = vmag2_strict(r.ux, r.uy); vnan |= (m2 != m2); vmax = fmaxf(vmax, m2); }
-                }
-            }
-            if (bottom) {  // j == 1 is always cell 1 of the first float4; the ring cell is cell 0
-                Cell r;
-                cell_rest(r);
-                bc_core(a.phys, 3, ig, ig, me, r, ramp);
-                if (a.code[(long long)il * pitch] & 1) refill(r);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) g[0][k] = r.f[k];
-                rho[0] = r.rho; ux[0] = r.ux; uy[0] = r.uy;
-            }
+            const float damp = fmaxf(dx, dy[c]);
+            if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
+            else collide_fast(a.phys, fin[c], damp, g[c]);
+            macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
         }
-    }
 
-    // ---- obstacle refill of interior cells (ref:452-455) and write-out ------------------------
-    // Cells of this float4: interior (refill by code), ring cells merged above (already final),
-    // padding j >= ny (zeros).  A float4 that starts on the top ring cell itself (ny-1 == j0) has
-    // no interior cell: its ring value is written by the owner of j = ny-2, so skip the store.
-    if (j0 != ny - 1) {
+        // ---- owners of ring cells keep a copy of their fresh un-refilled state (rare) ---------
+        const bool edge_col = (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
+        const bool touches_ring = (j0 == 0) || (j0 + kCellsPerThread >= ny - 1) || edge_col;
+        Cell own[kCellsPerThread];
+        if (touches_ring) {
 #pragma unroll
-    for (int c = 0; c < kCellsPerThread; ++c) {
-        const int j = j0 + c;
-        const bool interior = (j >= 1) && (j <= ny - 2);
-        if (interior && (code[c] & 1)) {
-            ux[c] = 0.0f; uy[c] = 0.0f;
+            for (int c = 0; c < kCellsPerThread; ++c) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+                for (int k = 0; k < 9; ++k) own[c].f[k] = g[c][k];
+                own[c].rho = rho[c]; own[c].ux = ux[c]; own[c].uy = uy[c];
+            }
         }
-        if (j >= ny) {
-            rho[c] = 0.0f; ux[c] = 0.0f; uy[c] = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) g[c][k] = 0.0f;
-        }
-    }
-    const long long o = (long long)il * pitch + j0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) st4(a.dst + k * plane + o, g[0][k], g[1][k], g[2][k], g[3][k]);
 
-    if (EMIT) {
-        st4(a.rho + o, rho[0], rho[1], rho[2], rho[3]);
-        st4(a.ux + o, ux[0], ux[1], ux[2], ux[3]);
-        st4(a.uy + o, uy[0], uy[1], uy[2], uy[3]);
+        // ---- obstacle refill of interior cells (ref:452-455) and float4 write-out -------------
+        // Non-interior slots of the float4 (ring row, padding) are overwritten / never read.
+        if (j0 != ny - 1) {
 #pragma unroll
-        for (int c = 0; c < kCellsPerThread; ++c) {
-            const float m2 = vmag2_strict(ux[c], uy[c]);
-            vnan |= (m2 != m2);
-            vmax = fmaxf(vmax, m2);
+            for (int c = 0; c < kCellsPerThread; ++c) {
+                const int j = j0 + c;
+                const bool interior = (j >= 1) && (j <= ny - 2);
+                if (interior && (code[c] & 1)) {
+                    ux[c] = 0.0f; uy[c] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+                }
+                if (!interior) {
+                    rho[c] = 0.0f; ux[c] = 0.0f; uy[c] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) g[c][k] = 0.0f;
+                }
+            }
+            const long long o = (long long)il * pitch + j0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st4(a.dst + k * plane + o, g[0][k], g[1][k], g[2][k], g[3][k]);
+            if (EMIT) {
+                st4(a.rho + o, rho[0], rho[1], rho[2], rho[3]);
+                st4(a.ux + o, ux[0], ux[1], ux[2], ux[3]);
+                st4(a.uy + o, uy[0], uy[1], uy[2], uy[3]);
+#pragma unroll
+                for (int c = 0; c < kCellsPerThread; ++c) {
+                    const float m2 = vmag2_strict(ux[c], uy[c]);
+                    vnan |= (m2 != m2);
+                    vmax = fmaxf(vmax, m2);
+                }
+            }
+        }
+
+        // ---- boundary ring (ref:438-450): scalar stores, after this thread's float4 stores -----
+        if (touches_ring) {
+            const int fc = *a.ctr_in + 1;
+            const float ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
+            TileSink sink;
+            sink.sm_f = nullptr;
+            sink.sm_mac = nullptr;
+            sink.il0 = sink.j0 = sink.bx = sink.by = sink.row_hi = sink.col_lo = sink.col_hi = 0;
+#pragma unroll
+            for (int c = 0; c < kCellsPerThread; ++c) {
+                const int j = j0 + c;
+                if (j < 1 || j > ny - 2) continue;
+                if (!(j == 1 || j == ny - 2 || edge_col)) continue;
+                ring_from_owner(a.ring, &sink, EMIT, il, j, &own[c], ramp, &vmax, &vnan);
+            }
         }
     }
-    }  // j0 != ny - 1
-    }  // live
 
     if (EMIT) {  // whole warp: max over lanes, one atomic per warp and only if it raises the running max
         for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
-        const bool any_nan = __any_sync(0xffffffffu, vnan);
+        const bool any_nan = __any_sync(0xffffffffu, vnan != 0);
         if (lane == 0) {
             const unsigned bits = __float_as_uint(vmax);
             if (bits > *a.maxv_bits) atomicMax(a.maxv_bits, bits);

@@ -1,0 +1,242 @@
+// Persistent TMA / mbarrier variant of the fused step (sm_100a).
+//
+// One CTA per SM loops over (BX x BY)-cell tiles.  A producer warp streams the 9 *already shifted*
+// source planes of the next tiles into a ring of shared-memory stages with
+// cp.async.bulk.tensor (TMA): plane k is fetched at tile origin - e_k, so the hardware does the
+// pull-streaming, including the unaligned +-1 shift in y that costs shuffles and edge loads in the
+// register variant, and zero-fills out-of-range coordinates.  Consumer warps collide one cell per
+// thread from shared memory into an output tile, which one thread hands back to TMA
+// (cp.async.bulk.tensor shared -> global).  Loads, math and stores of different tiles overlap; the
+// bytes in flight per SM are set by the stage count, not by registers or occupancy.
+#pragma once
+#include <cuda.h>
+
+#include "lbm2d_kernels.cuh"
+
+namespace lbm {
+
+constexpr int kTileBX = 8;     // columns per tile
+constexpr int kTileBY = 128;   // rows per tile (fast dimension, 512-byte TMA rows)
+constexpr int kTileCells = kTileBX * kTileBY;
+constexpr int kInStages = 3;
+constexpr int kOutStages = 2;
+constexpr int kConsumerWarps = 16;
+constexpr int kTmaThreads = 32 * (1 + kConsumerWarps);
+constexpr int kStageInBytes = 9 * kTileCells * 4 + kTileCells;       // 9 fp32 planes + 1 byte cell codes
+constexpr int kStageInStride = (kStageInBytes + 127) / 128 * 128;
+constexpr int kStageOutBytes = 12 * kTileCells * 4;                   // 9 f planes + rho, ux, uy
+constexpr int kTmaSmemBytes = kInStages * kStageInStride + kOutStages * kStageOutBytes + 1024;
+
+struct TmaArgs {
+    const float *__restrict__ damp_x;
+    const float *__restrict__ damp_y;
+    const float *__restrict__ ramp_tab;
+    const int *ctr_in;
+    int *ctr_out;
+    unsigned *maxv_bits;
+    const RingCtx *ring;
+    int nx_local, ny, pitch;
+    int n_tx, n_ty, n_tiles;
+    int col_lo, col_hi, row_hi;   // store-tensor extent (local columns [col_lo, col_hi), rows [0, row_hi))
+    int west_ring, east_ring;
+    int warmup;
+    Physics phys;
+};
+
+// ---- thin PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+}
+
+// Tensor maps (all fp32 except the cell codes), built on the host by lbm2d_capi.cu:
+//   map_src : 3-D (pitch, nx_local, 9) over the source buffer, box (BY, BX, 1)
+//   map_code: 2-D (pitch, nx_local) uint8, box (BY, BX)
+//   map_dst : 3-D (row_hi, col_hi - col_lo, 9) over the destination buffer starting at column col_lo
+//   map_mac : 3-D (row_hi, col_hi - col_lo, 3) over the rho / ux / uy planes (EMIT)
+template <bool STRICT, bool EMIT>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_code,
+                const __grid_constant__ CUtensorMap map_dst, const __grid_constant__ CUtensorMap map_mac,
+                const TmaArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *in_base = smem;
+    float *out_base = reinterpret_cast<float *>(smem + kInStages * kStageInStride);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kInStages * kStageInStride + kOutStages * kStageOutBytes);
+    uint64_t *full = bars, *empty = bars + kInStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kInStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===================== producer: TMA loads of the shifted planes =========================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+                const int s = it % kInStages;
+                const uint32_t ph = (it / kInStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int il0 = a.col_lo + (t / a.n_ty) * kTileBX, j0 = (t % a.n_ty) * kTileBY;
+                unsigned char *st = in_base + s * kStageInStride;
+                mbar_expect_tx(&full[s], kStageInBytes);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    tma_load_3d(st + k * kTileCells * 4, &map_src, j0 - kEy[k], il0 - kEx[k], k, &full[s]);
+                tma_load_2d(st + 9 * kTileCells * 4, &map_code, j0, il0, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ========================= consumers: collide from smem, write the output tile ===============
+    const int ctid = threadIdx.x - 32;  // 0 .. kConsumerWarps*32-1
+    const int ny = a.ny;
+    float vmax = 0.0f;
+    int vnan = 0;
+    float ramp = 0.0f;
+    {
+        const int fc = *a.ctr_in + 1;
+        ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
+    }
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+        const int s = it % kInStages;
+        const uint32_t ph = (it / kInStages) & 1;
+        const int o = it % kOutStages;
+        const int il0 = a.col_lo + (t / a.n_ty) * kTileBX, j0 = (t % a.n_ty) * kTileBY;
+        const float *in = reinterpret_cast<const float *>(in_base + s * kStageInStride);
+        const unsigned char *codes = in_base + s * kStageInStride + 9 * kTileCells * 4;
+        float *out = out_base + o * (kStageOutBytes / 4);
+
+        TileSink sink;
+        sink.sm_f = out;
+        sink.sm_mac = out + 9 * kTileCells;
+        sink.il0 = il0; sink.j0 = j0; sink.bx = kTileBX; sink.by = kTileBY;
+        sink.row_hi = a.row_hi; sink.col_lo = a.col_lo; sink.col_hi = a.col_hi;
+
+        mbar_wait(&full[s], ph);
+#pragma unroll 1
+        for (int c = ctid; c < kTileCells; c += kConsumerWarps * 32) {
+            const int x = c / kTileBY, y = c % kTileBY;
+            const int il = il0 + x, j = j0 + y;
+            const bool interior = (il >= 1) && (il <= a.nx_local - 2) && (j >= 1) && (j <= ny - 2);
+            if (!interior) continue;  // ring cells are written by their owners, the rest is clipped by the store
+            float fin[9], g[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) fin[k] = in[k * kTileCells + c];
+            const float damp = fmaxf(__ldg(a.damp_x + il), __ldg(a.damp_y + j));
+            if (STRICT) collide_strict(a.phys, fin, damp, g);
+            else collide_fast(a.phys, fin, damp, g);
+            float rho, ux, uy;
+            macro_from_f<STRICT>(g, rho, ux, uy);
+            const bool owner = (j == 1) || (j == ny - 2) || (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
+            if (owner) {  // rare: produce the ring cells hanging off this cell from its un-refilled state
+                Cell me;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) me.f[k] = g[k];
+                me.rho = rho; me.ux = ux; me.uy = uy;
+                ring_from_owner(a.ring, &sink, EMIT, il, j, &me, ramp, &vmax, &vnan);
+            }
+            if (codes[c] & 1) {  // obstacle refill, ref:452-455
+                ux = 0.0f; uy = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) g[k] = __fmul_rn(kW[k], rho);
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k * kTileCells + c] = g[k];
+            if (EMIT) {
+                out[9 * kTileCells + c] = rho;
+                out[10 * kTileCells + c] = ux;
+                out[11 * kTileCells + c] = uy;
+                const float m2 = vmag2_strict(ux, uy);
+                vnan |= (m2 != m2);
+                vmax = fmaxf(vmax, m2);
+            }
+        }
+        // input stage consumed: hand it back to the producer (one arrival per consumer warp)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        // output tile complete: make the generic-proxy writes visible to TMA, then one thread stores
+        fence_async_smem();
+        consumer_bar();
+        if (ctid == 0) {
+            const int sx = il0 - a.col_lo;  // store-tensor column coordinate
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tma_store_3d(&map_dst, j0, sx, k, out + k * kTileCells);
+            if (EMIT) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tma_store_3d(&map_mac, j0, sx, k, out + (9 + k) * kTileCells);
+            }
+            tma_commit();
+            tma_wait_read<kOutStages - 1>();  // the OTHER output stage is free again
+        }
+        consumer_bar();
+    }
+    if (ctid == 0) tma_wait_all<0>();  // all stores of this CTA have landed before the grid ends
+
+    if (EMIT) {
+        for (int sft = 16; sft > 0; sft >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
+        const bool any_nan = __any_sync(0xffffffffu, vnan != 0);
+        if (lane == 0) {
+            const unsigned bits = __float_as_uint(vmax);
+            if (bits > *a.maxv_bits) atomicMax(a.maxv_bits, bits);
+            if (any_nan) a.maxv_bits[1] = 1u;
+        }
+    }
+}
+
+}  // namespace lbm

@@ -27,12 +27,13 @@ class _FieldShim:
 
 
 class LBM2D_MRT_LES:
-    def __init__(self, config, mask_data=None, *, arith="fast", device=None, slab=None):
+    def __init__(self, config, mask_data=None, *, arith="fast", kernel="auto", device=None, slab=None):
         """ref:13-29.  `config` is the per-case YAML dict; missing keys raise KeyError like the
         reference.  `mask_data`: bool/float (nx, ny), True/1 = solid, None = all fluid (ref:107-111).
 
         Extensions (keyword-only, absent from the reference): `arith` = "fast" | "strict"
-        (strict is bit-identical to the fp32 oracle), `device` = CUDA ordinal, `slab` =
+        (strict is bit-identical to the fp32 oracle), `kernel` = "auto" | "register" | "tma",
+        `device` = CUDA ordinal, `slab` =
         (x0, nx_owned) to own a column range of a larger global domain (multi-GPU).
         """
         self.config = config
@@ -64,6 +65,7 @@ class LBM2D_MRT_LES:
             p.bc_value[d][0] = float(bc_value[d][0])
             p.bc_value[d][1] = float(bc_value[d][1])
         p.arith = _capi.ARITH[arith]
+        p.kernel = _capi.KERNEL[kernel]
         p.obstacle_mode = 0
         p.device = -1 if device is None else int(device)
         p.nx_global, p.slab_x0 = self.nx, x0

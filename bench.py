@@ -183,7 +183,7 @@ def run_ours(args):
         slabs = import_module("01-lbm-2d_b200.slab")
         solver = slabs.SlabLBM(cfg, mask, rank=rank, world=world, device=local_rank)
     else:
-        solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="fast", device=local_rank)
+        solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=args.arith, device=local_rank)
     solver.init()
     view = solver.device_view()
     stream = torch.cuda.ExternalStream(view.stream, device=torch.device("cuda", local_rank))
@@ -219,6 +219,8 @@ def run_ours(args):
     css = cfg["simulation"]["compute_step_size"]
     interval = cfg["outputs"]["dataset"]["interval_steps"]
     n_batches = max(1, min(4, args.steps // css if args.steps >= css else 1))
+    if args.quick:
+        n_batches, css, interval = 1, 1, 10**9
     barrier()
     t0 = time.perf_counter()
     d2h = 0
@@ -246,7 +248,8 @@ def run_ours(args):
     cells_per_gpu = nx * ny / world
     avg_kernel_s = ms * 1e-3 / args.steps
     achieved = ALGO_BYTES_PER_CELL * cells_per_gpu / avg_kernel_s / 1e9
-    cpu_mlups, cores, cpu_n, cpu_dt = time_cpu_port(*build_workload(args.workload, 1), budget_s=15.0) if world == 1 else (None, None, None, None)
+    cpu_mlups, cores, cpu_n, cpu_dt = (time_cpu_port(*build_workload(args.workload, 1), budget_s=15.0)
+                                       if world == 1 and not args.quick else (None, None, None, None))
     line = {
         "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -255,7 +258,7 @@ def run_ours(args):
             "workload": f"{args.workload} {nx}x{ny} (BASELINE configs[2] per GPU), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
             "grid": [nx, ny], "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, 1 halo column / step",
             "l2_policy": "working set 1.22 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
-            "arith": "fast", "solid_fraction": float(mask.mean()),
+            "arith": args.arith, "solid_fraction": float(mask.mean()),
         },
         "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / done,
                 "what": f"{n_batches} batches of run_step({css}) + get_force + get_max_velocity + get_moments_numpy every {interval} steps"},
@@ -278,6 +281,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank"])
+    ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e / cpu_baseline legs")
+    ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

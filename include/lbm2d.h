@@ -47,6 +47,12 @@ typedef enum {
 } LbmArith;
 
 typedef enum {
+    LBM_KERNEL_AUTO = 0,     /* TMA variant on grids large enough to fill the GPU, register variant otherwise */
+    LBM_KERNEL_REGISTER = 1, /* one warp per 128-cell column segment, float4 loads + warp shuffles */
+    LBM_KERNEL_TMA = 2       /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
+} LbmKernel;
+
+typedef enum {
     LBM_OBSTACLE_REFILL = 0 /* wet-node equilibrium refill, ref:452-455 (what the reference does) */
 } LbmObstacleMode;
 
@@ -69,6 +75,7 @@ typedef struct {
     int32_t arith;           /* LbmArith */
     int32_t obstacle_mode;   /* LbmObstacleMode */
     int32_t device;          /* CUDA device ordinal, -1 = current device */
+    int32_t kernel;          /* LbmKernel */
     /* x-slab decomposition (single GPU: nx_global = nx, slab_x0 = 0).  A slab owns global columns
      * [slab_x0, slab_x0 + nx); `nx` above is then the OWNED width, and one halo column is kept on
      * every side that is not a domain boundary. */

@@ -74,3 +74,29 @@ def rel_linf(a, b):
     b = np.asarray(b, np.float64)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+_EX = (0, 1, 0, -1, 0, 1, -1, -1, 1)
+_EY = (0, 0, 1, 0, -1, 1, 1, -1, -1)
+_INV = (0, 3, 4, 1, 2, 7, 8, 5, 6)
+
+
+def force_f64(f_new, mask):
+    """Momentum-exchange force (reference LBM2D_MRT_LES.py:588-641) summed exactly-ish in float64, and
+    S = sum of |terms|.  The reference adds fp32 terms in an unspecified (atomic) order, and the terms
+    cancel to a small net force, so two correct fp32 summations may differ by ~n * eps * S."""
+    solid = np.asarray(mask, bool)
+    nx, ny = solid.shape
+    F = np.zeros(2, np.float64)
+    S = 0.0
+    for k in range(1, 9):
+        ex, ey = _EX[k], _EY[k]
+        # solid at (i, j), fluid neighbour at (i + ex, j + ey), both in bounds
+        i0, i1 = max(0, -ex), min(nx, nx - ex)
+        j0, j1 = max(0, -ey), min(ny, ny - ey)
+        s = solid[i0:i1, j0:j1] & ~solid[i0 + ex:i1 + ex, j0 + ey:j1 + ey]
+        fv = 2.0 * f_new[i0 + ex:i1 + ex, j0 + ey:j1 + ey, _INV[k]].astype(np.float64)[s]
+        F[0] += -ex * fv.sum()
+        F[1] += -ey * fv.sum()
+        S += np.abs(fv).sum()
+    return F, S

@@ -43,9 +43,9 @@ def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "lbm2d.h"\n'
-        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(LbmParams), offsetof(LbmParams, nu),"
+        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(LbmParams), offsetof(LbmParams, nu),"
         " offsetof(LbmParams, sponge_in), offsetof(LbmParams, sponge_strength), offsetof(LbmParams, bc_type),"
-        " offsetof(LbmParams, bc_value), offsetof(LbmParams, arith), offsetof(LbmParams, slab_x0));"
+        " offsetof(LbmParams, bc_value), offsetof(LbmParams, arith), offsetof(LbmParams, kernel), offsetof(LbmParams, slab_x0));"
         "printf(\"%zu %zu %zu\\n\", sizeof(LbmDeviceView), offsetof(LbmDeviceView, nx_local), offsetof(LbmDeviceView, stream));return 0;}\n"
     )
     exe = tmp_path / "layout"
@@ -53,7 +53,7 @@ def test_struct_layout_matches_c(tmp_path):
     a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     P, V = capi.LbmParams, capi.LbmDeviceView
     assert [int(x) for x in a.split()] == [C.sizeof(P), P.nu.offset, P.sponge_in.offset, P.sponge_strength.offset,
-                                           P.bc_type.offset, P.bc_value.offset, P.arith.offset, P.slab_x0.offset]
+                                           P.bc_type.offset, P.bc_value.offset, P.arith.offset, P.kernel.offset, P.slab_x0.offset]
     assert [int(x) for x in b.split()] == [C.sizeof(V), V.nx_local.offset, V.stream.offset]
 
 
