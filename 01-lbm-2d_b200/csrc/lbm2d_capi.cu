@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -51,7 +52,7 @@ struct LbmSolver {
     lbm::RingCtx *ring_ctx = nullptr;  // [2], one per destination buffer
     bool use_tma = false;
     int tma_grid = 0;
-    CUtensorMap map_src[2], map_dst[2], map_code, map_mac;
+    CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
     lbm::TmaArgs tma_args{};
     lbm::Link *links = nullptr;
     int n_links = 0;
@@ -198,6 +199,8 @@ int setup_tma(LbmSolver *s) {
         const cuuint64_t dsrc[3] = {(cuuint64_t)s->pitch, (cuuint64_t)s->nx_local, 9};
         const cuuint64_t st[2] = {pitch_b, plane_b};
         if (int rc = encode_map(&s->map_src[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b], dsrc, st, box3)) return rc;
+        const cuuint32_t box3h[3] = {(cuuint32_t)kRowHalo, (cuuint32_t)kTileBX, 1};
+        if (int rc = encode_map(&s->map_srch[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b], dsrc, st, box3h)) return rc;
         const cuuint64_t ddst[3] = {(cuuint64_t)row_hi, (cuuint64_t)(col_hi - col_lo), 9};
         if (int rc = encode_map(&s->map_dst[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b] + (size_t)col_lo * s->pitch, ddst, st, box3))
             return rc;
@@ -472,15 +475,15 @@ int lbm_run(LbmHandle h, int steps) {
             ta.ctr_in = h->ctr + par;
             ta.ctr_out = h->ctr + (par ^ 1);
             ta.ring = h->ring_ctx + (par ^ 1);
-            const CUtensorMap &ms = h->map_src[par], &md = h->map_dst[par ^ 1];
+            const CUtensorMap &ms = h->map_src[par], &mh = h->map_srch[par], &md = h->map_dst[par ^ 1];
             const dim3 grid(h->tma_grid), block(lbm::kTmaThreads);
             const size_t sm = lbm::kTmaSmemBytes;
             if (strict) {
-                if (emit) lbm::step_tma_kernel<true, true><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
-                else lbm::step_tma_kernel<true, false><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+                if (emit) lbm::step_tma_kernel<true, true><<<grid, block, sm, h->stream>>>(ms, mh, h->map_code, md, h->map_mac, ta);
+                else lbm::step_tma_kernel<true, false><<<grid, block, sm, h->stream>>>(ms, mh, h->map_code, md, h->map_mac, ta);
             } else {
-                if (emit) lbm::step_tma_kernel<false, true><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
-                else lbm::step_tma_kernel<false, false><<<grid, block, sm, h->stream>>>(ms, h->map_code, md, h->map_mac, ta);
+                if (emit) lbm::step_tma_kernel<false, true><<<grid, block, sm, h->stream>>>(ms, mh, h->map_code, md, h->map_mac, ta);
+                else lbm::step_tma_kernel<false, false><<<grid, block, sm, h->stream>>>(ms, mh, h->map_code, md, h->map_mac, ta);
             }
             h->steps_done++;
             h->launches++;

@@ -22,7 +22,16 @@ constexpr int kInStages = 3;
 constexpr int kOutStages = 2;
 constexpr int kConsumerWarps = 16;
 constexpr int kTmaThreads = 32 * (1 + kConsumerWarps);
-constexpr int kStageInBytes = 9 * kTileCells * 4 + kTileCells;       // 9 fp32 planes + 1 byte cell codes
+// TMA needs a 16-byte aligned start address, so the +-1 float shift of the pull in y cannot be put
+// into the box origin.  Planes with e_ky != 0 are fetched with a 4-float apron on both sides of the
+// tile rows (aligned origin j0 - 4, rows of BY + 8 floats) and read at offset 4 - e_ky; the shift in
+// x is a whole row of the tensor and goes into the box origin directly.
+constexpr int kHaloY = 4;
+constexpr int kRowHalo = kTileBY + 2 * kHaloY;
+__host__ __device__ constexpr int plane_row(int k) { return (k == 2 || k >= 4) ? kRowHalo : kTileBY; }   // e_ky != 0 for k = 2,4,5,6,7,8
+__host__ __device__ constexpr int plane_off(int k) { return k == 0 ? 0 : plane_off(k - 1) + plane_row(k - 1) * kTileBX; }  // floats
+constexpr int kCodeOff = plane_off(9) * 4;                            // byte offset of the cell-code tile
+constexpr int kStageInBytes = kCodeOff + kTileCells;                  // 9 fp32 planes + 1 byte cell codes
 constexpr int kStageInStride = (kStageInBytes + 127) / 128 * 128;
 constexpr int kStageOutBytes = 12 * kTileCells * 4;                   // 9 f planes + rho, ux, uy
 constexpr int kTmaSmemBytes = kInStages * kStageInStride + kOutStages * kStageOutBytes + 1024;
@@ -96,13 +105,15 @@ __device__ __forceinline__ void consumer_bar() {
 }
 
 // Tensor maps (all fp32 except the cell codes), built on the host by lbm2d_capi.cu:
-//   map_src : 3-D (pitch, nx_local, 9) over the source buffer, box (BY, BX, 1)
+//   map_src : 3-D (pitch, nx_local, 9) over the source buffer, box (BY, BX, 1)      (planes with e_ky == 0)
+//   map_srch: same tensor, box (BY + 8, BX, 1)                                       (planes with e_ky != 0)
 //   map_code: 2-D (pitch, nx_local) uint8, box (BY, BX)
 //   map_dst : 3-D (row_hi, col_hi - col_lo, 9) over the destination buffer starting at column col_lo
 //   map_mac : 3-D (row_hi, col_hi - col_lo, 3) over the rho / ux / uy planes (EMIT)
 template <bool STRICT, bool EMIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_code,
+step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_srch,
+                const __grid_constant__ CUtensorMap map_code,
                 const __grid_constant__ CUtensorMap map_dst, const __grid_constant__ CUtensorMap map_mac,
                 const TmaArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -134,9 +145,11 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
                 unsigned char *st = in_base + s * kStageInStride;
                 mbar_expect_tx(&full[s], kStageInBytes);
 #pragma unroll
-                for (int k = 0; k < 9; ++k)
-                    tma_load_3d(st + k * kTileCells * 4, &map_src, j0 - kEy[k], il0 - kEx[k], k, &full[s]);
-                tma_load_2d(st + 9 * kTileCells * 4, &map_code, j0, il0, &full[s]);
+                for (int k = 0; k < 9; ++k) {
+                    if (kEy[k] == 0) tma_load_3d(st + plane_off(k) * 4, &map_src, j0, il0 - kEx[k], k, &full[s]);
+                    else tma_load_3d(st + plane_off(k) * 4, &map_srch, j0 - kHaloY, il0 - kEx[k], k, &full[s]);
+                }
+                tma_load_2d(st + kCodeOff, &map_code, j0, il0, &full[s]);
             }
         }
         return;
@@ -159,7 +172,7 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         const int o = it % kOutStages;
         const int il0 = a.col_lo + (t / a.n_ty) * kTileBX, j0 = (t % a.n_ty) * kTileBY;
         const float *in = reinterpret_cast<const float *>(in_base + s * kStageInStride);
-        const unsigned char *codes = in_base + s * kStageInStride + 9 * kTileCells * 4;
+        const unsigned char *codes = in_base + s * kStageInStride + kCodeOff;
         float *out = out_base + o * (kStageOutBytes / 4);
 
         TileSink sink;
@@ -177,7 +190,8 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             if (!interior) continue;  // ring cells are written by their owners, the rest is clipped by the store
             float fin[9], g[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) fin[k] = in[k * kTileCells + c];
+            for (int k = 0; k < 9; ++k)
+                fin[k] = in[plane_off(k) + x * plane_row(k) + y + (kEy[k] == 0 ? 0 : kHaloY - kEy[k])];
             const float damp = fmaxf(__ldg(a.damp_x + il), __ldg(a.damp_y + j));
             if (STRICT) collide_strict(a.phys, fin, damp, g);
             else collide_fast(a.phys, fin, damp, g);

@@ -183,7 +183,7 @@ def run_ours(args):
         slabs = import_module("01-lbm-2d_b200.slab")
         solver = slabs.SlabLBM(cfg, mask, rank=rank, world=world, device=local_rank)
     else:
-        solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=args.arith, device=local_rank)
+        solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=args.arith, kernel=args.kernel, device=local_rank)
     solver.init()
     view = solver.device_view()
     stream = torch.cuda.ExternalStream(view.stream, device=torch.device("cuda", local_rank))
@@ -258,7 +258,7 @@ def run_ours(args):
             "workload": f"{args.workload} {nx}x{ny} (BASELINE configs[2] per GPU), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
             "grid": [nx, ny], "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, 1 halo column / step",
             "l2_policy": "working set 1.22 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
-            "arith": args.arith, "solid_fraction": float(mask.mean()),
+            "arith": args.arith, "kernel": args.kernel, "solid_fraction": float(mask.mean()),
         },
         "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / done,
                 "what": f"{n_batches} batches of run_step({css}) + get_force + get_max_velocity + get_moments_numpy every {interval} steps"},
@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank"])
     ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e / cpu_baseline legs")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

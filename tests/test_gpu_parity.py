@@ -28,9 +28,10 @@ def _force_close(force, f_new, mask, rel=2e-6):
     """CUDA force (fp64 tree sum of the fp32 link terms) against the float64 sum over the oracle's f_new.
     Tolerance is relative to S = sum |terms| because the net force is a cancellation of O(S) terms
     (the oracle's own sequential fp32 sum carries ~1e-5 S of rounding noise, see helpers.force_f64)."""
-    if not np.isfinite(f_new).all():
+    with np.errstate(all="ignore"):
+        F, S = force_f64(f_new, mask if mask is not None else np.zeros(f_new.shape[:2], bool))
+    if not np.isfinite(F).all():
         return not np.isfinite(force).all()
-    F, S = force_f64(f_new, mask if mask is not None else np.zeros(f_new.shape[:2], bool))
     return float(np.max(np.abs(np.asarray(force, np.float64) - F))) <= rel * S + 1e-9
 
 
