@@ -51,6 +51,7 @@ struct LbmSolver {
     unsigned *maxv = nullptr;
     lbm::RingCtx *ring_ctx = nullptr;  // [2], one per destination buffer
     bool use_tma = false;
+    int vwidth = 4;  // cells per thread of the register variant
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
     lbm::TmaArgs tma_args{};
@@ -202,13 +203,15 @@ int setup_tma(LbmSolver *s) {
         const cuuint32_t box3h[3] = {(cuuint32_t)kRowHalo, (cuuint32_t)kTileBX, 1};
         if (int rc = encode_map(&s->map_srch[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b], dsrc, st, box3h)) return rc;
         const cuuint64_t ddst[3] = {(cuuint64_t)row_hi, (cuuint64_t)(col_hi - col_lo), 9};
-        if (int rc = encode_map(&s->map_dst[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b] + (size_t)col_lo * s->pitch, ddst, st, box3))
+        const cuuint32_t box9[3] = {(cuuint32_t)kTileBY, (cuuint32_t)kTileBX, 9};
+        if (int rc = encode_map(&s->map_dst[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->f[b] + (size_t)col_lo * s->pitch, ddst, st, box9))
             return rc;
     }
     {
         const cuuint64_t d[3] = {(cuuint64_t)row_hi, (cuuint64_t)(col_hi - col_lo), 3};
         const cuuint64_t st[2] = {pitch_b, plane_b};
-        if (int rc = encode_map(&s->map_mac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->mac + (size_t)col_lo * s->pitch, d, st, box3)) return rc;
+        const cuuint32_t box3m[3] = {(cuuint32_t)kTileBY, (cuuint32_t)kTileBX, 3};
+        if (int rc = encode_map(&s->map_mac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->mac + (size_t)col_lo * s->pitch, d, st, box3m)) return rc;
         const cuuint64_t dc[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->nx_local};
         const cuuint64_t stc[1] = {(cuuint64_t)s->pitch};
         const cuuint32_t box2[2] = {(cuuint32_t)kTileBY, (cuuint32_t)kTileBX};
@@ -303,7 +306,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     s->ny = p.ny;
     s->pitch = round_up(p.ny, 32);
     s->plane = (long long)s->nx_local * s->pitch;
-    s->nseg = (s->pitch + lbm::kSegCells - 1) / lbm::kSegCells;
+    s->vwidth = (p.kernel == LBM_KERNEL_REGISTER2) ? 2 : (p.kernel == LBM_KERNEL_REGISTER1 ? 1 : 4);
+    s->nseg = (s->pitch + 32 * s->vwidth - 1) / (32 * s->vwidth);
     s->n_items = (s->nx_local - 2) * s->nseg;
 
     // fp32 constants, derived like the reference's Python scope + Taichi f32 casts
@@ -427,7 +431,7 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         s->use_tma = p.kernel == LBM_KERNEL_TMA || (p.kernel == LBM_KERNEL_AUTO && tiles >= 4LL * sms);
-        if (p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER && p.kernel != LBM_KERNEL_TMA) {
+        if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_REGISTER1) {
             delete s;
             return fail(LBM_ERR_INVALID, "unsupported kernel variant");
         }
@@ -490,13 +494,17 @@ int lbm_run(LbmHandle h, int steps) {
             continue;
         }
         const lbm::StepArgs a = make_args(h);
-        if (strict) {
-            if (emit) lbm::step_kernel<true, true><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
-            else lbm::step_kernel<true, false><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
-        } else {
-            if (emit) lbm::step_kernel<false, true><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
-            else lbm::step_kernel<false, false><<<blocks, lbm::kThreads, 0, h->stream>>>(a);
-        }
+#define LBM_LAUNCH_REG(S, E, V) lbm::step_kernel<S, E, V><<<blocks, lbm::kThreads, 0, h->stream>>>(a)
+#define LBM_LAUNCH_V(V)                                                     \
+    do {                                                                    \
+        if (strict) { if (emit) LBM_LAUNCH_REG(true, true, V); else LBM_LAUNCH_REG(true, false, V); } \
+        else { if (emit) LBM_LAUNCH_REG(false, true, V); else LBM_LAUNCH_REG(false, false, V); }      \
+    } while (0)
+        if (h->vwidth == 4) LBM_LAUNCH_V(4);
+        else if (h->vwidth == 2) LBM_LAUNCH_V(2);
+        else LBM_LAUNCH_V(1);
+#undef LBM_LAUNCH_V
+#undef LBM_LAUNCH_REG
         h->steps_done++;
         h->launches++;
     }

@@ -10,8 +10,6 @@ namespace lbm {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kCellsPerThread = 4;
-constexpr int kSegCells = 32 * kCellsPerThread;  // cells of one column handled by one warp
 
 struct StepArgs {
     const float *__restrict__ src;  // 9 planes
@@ -42,75 +40,101 @@ __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
     return __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy));
 }
 
+// aligned V-wide global accesses (V = 1, 2, 4 floats)
+template <int V>
+__device__ __forceinline__ void ldv(const float *p, float (&o)[V]) {
+    if (V == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
+    else if (V == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
+    else o[0] = __ldg(p);
+}
+template <int V>
+__device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
+    if (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+    else if (V == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1 % V]);
+    else *p = o[0];
+}
+template <int V>
+__device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) {
+    if (V == 4) { const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
+    else if (V == 2) { const uchar2 t = __ldg(reinterpret_cast<const uchar2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
+    else o[0] = __ldg(p);
+}
+
 // One fused pass: pull-stream, MRT-LES collision, sponge, macroscopic update, boundary ring,
 // obstacle refill (ref:552-573 = collide_and_stream + update_macro_var + apply_bc), f_src -> f_dst.
 //
-// "Register" variant.  Work decomposition: one warp = one 128-cell segment of one interior column;
-// one thread = 4 consecutive cells in y (128-bit accesses).  The +-1 shift of the pull in y comes
-// from the neighbouring lane by warp shuffle, with one extra scalar load at each end of the
-// segment (issued up front with the vector loads).  Ring cells are produced by the thread that owns
-// their interior neighbour (ring_from_owner) and written with scalar stores after the float4 stores.
-template <bool STRICT, bool EMIT>
-__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
+// "Register" variant.  Work decomposition: one warp = one (32 V)-cell segment of one interior column;
+// one thread = V consecutive cells in y (V = 4: 128-bit accesses).  Every access is aligned and fully
+// coalesced; the +-1 shift of the pull in y comes from the neighbouring lane by warp shuffle, with
+// one extra scalar load at each end of the segment (issued up front with the vector loads).  Ring
+// cells are produced by the thread that owns their interior neighbour (ring_from_owner) and written
+// with scalar stores after the vector stores.
+template <bool STRICT, bool EMIT, int V>
+__global__ void __launch_bounds__(kThreads, (V == 4 ? 2 : (V == 2 ? 4 : 6))) step_kernel(const StepArgs a) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
     if (item >= a.n_items) return;                                          // warp-uniform
     const int il = 1 + item / a.nseg;                                        // local column
-    const int j0 = (item % a.nseg) * kSegCells + lane * kCellsPerThread;
+    const int j0 = (item % a.nseg) * (32 * V) + lane * V;
     const bool lane_on = j0 < a.pitch;
     const int ny = a.ny, pitch = a.pitch;
     const long long plane = a.plane;
 
     // ---- pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky) -----------------------
     // phase 1: every load of this thread is issued before the first use
-    float4 v[9];
+    float v[9][V];
     float edge[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const float *col = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < V; ++c) v[k][c] = 0.f;
         edge[k] = 0.f;
-        if (lane_on) v[k] = ldg4(col + j0);
+        if (lane_on) ldv<V>(col + j0, v[k]);
         if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = __ldg(col + j0 - 1);
-        if (kEy[k] == -1 && lane == 31 && j0 + 4 < ny) edge[k] = __ldg(col + j0 + 4);
+        if (kEy[k] == -1 && lane == 31 && j0 + V < ny) edge[k] = __ldg(col + j0 + V);
     }
     const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
     float dx = 0.f;
-    float4 dy4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    uchar4 code4 = make_uchar4(0, 0, 0, 0);
+    float dy[V];
+    unsigned char code[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; }
     if (live) {
         dx = __ldg(a.damp_x + il);
-        dy4 = ldg4(a.damp_y + j0);
-        code4 = __ldg(reinterpret_cast<const uchar4 *>(a.code + (long long)il * pitch + j0));
+        ldv<V>(a.damp_y + j0, dy);
+        ldcode<V>(a.code + (long long)il * pitch + j0, code);
     }
     // phase 2: assemble the shifted rows
-    float fin[kCellsPerThread][9];
+    float fin[V][9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         if (kEy[k] == 0) {
-            fin[0][k] = v[k].x; fin[1][k] = v[k].y; fin[2][k] = v[k].z; fin[3][k] = v[k].w;
+#pragma unroll
+            for (int c = 0; c < V; ++c) fin[c][k] = v[k][c];
         } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
-            float below = __shfl_up_sync(0xffffffffu, v[k].w, 1);
+            float below = __shfl_up_sync(0xffffffffu, v[k][V - 1], 1);
             if (lane == 0) below = edge[k];
-            fin[0][k] = below; fin[1][k] = v[k].x; fin[2][k] = v[k].y; fin[3][k] = v[k].z;
+            fin[0][k] = below;
+#pragma unroll
+            for (int c = 1; c < V; ++c) fin[c][k] = v[k][c - 1];
         } else {                   // needs j+1: first element of the lane above
-            float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
+            float above = __shfl_down_sync(0xffffffffu, v[k][0], 1);
             if (lane == 31) above = edge[k];
-            fin[0][k] = v[k].y; fin[1][k] = v[k].z; fin[2][k] = v[k].w; fin[3][k] = above;
+#pragma unroll
+            for (int c = 0; c < V - 1; ++c) fin[c][k] = v[k][c + 1];
+            fin[V - 1][k] = above;
         }
     }
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
     if (live) {
-        const float dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
-        const unsigned char code[4] = {code4.x, code4.y, code4.z, code4.w};
-
         // ---- collide + macro (ref:266-436) --------------------------------------------------
-        float g[kCellsPerThread][9];
-        float rho[kCellsPerThread], ux[kCellsPerThread], uy[kCellsPerThread];
+        float g[V][9];
+        float rho[V], ux[V], uy[V];
 #pragma unroll
-        for (int c = 0; c < kCellsPerThread; ++c) {
+        for (int c = 0; c < V; ++c) {
             const float damp = fmaxf(dx, dy[c]);
             if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
             else collide_fast(a.phys, fin[c], damp, g[c]);
@@ -119,22 +143,27 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
 
         // ---- owners of ring cells keep a copy of their fresh un-refilled state (rare) ---------
         const bool edge_col = (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
-        const bool touches_ring = (j0 == 0) || (j0 + kCellsPerThread >= ny - 1) || edge_col;
-        Cell own[kCellsPerThread];
+        const bool touches_ring = (j0 <= 1) || (j0 + V >= ny - 1) || edge_col;
+        Cell own[V];
         if (touches_ring) {
 #pragma unroll
-            for (int c = 0; c < kCellsPerThread; ++c) {
+            for (int c = 0; c < V; ++c) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) own[c].f[k] = g[c][k];
                 own[c].rho = rho[c]; own[c].ux = ux[c]; own[c].uy = uy[c];
             }
         }
 
-        // ---- obstacle refill of interior cells (ref:452-455) and float4 write-out -------------
-        // Non-interior slots of the float4 (ring row, padding) are overwritten / never read.
-        if (j0 != ny - 1) {
+        // ---- obstacle refill of interior cells (ref:452-455) and vector write-out -------------
+        // A vector made only of ring / padding cells is not written (their owners write the ring cells);
+        // otherwise non-interior slots are written as 0 and the ring slots are overwritten below by
+        // the owner -- this same thread whenever the vector holds both the ring cell and its owner.
+        bool any_interior = false;
 #pragma unroll
-            for (int c = 0; c < kCellsPerThread; ++c) {
+        for (int c = 0; c < V; ++c) any_interior |= (j0 + c >= 1) && (j0 + c <= ny - 2);
+        if (any_interior) {
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
                 const int j = j0 + c;
                 const bool interior = (j >= 1) && (j <= ny - 2);
                 if (interior && (code[c] & 1)) {
@@ -150,13 +179,18 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
             }
             const long long o = (long long)il * pitch + j0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) st4(a.dst + k * plane + o, g[0][k], g[1][k], g[2][k], g[3][k]);
-            if (EMIT) {
-                st4(a.rho + o, rho[0], rho[1], rho[2], rho[3]);
-                st4(a.ux + o, ux[0], ux[1], ux[2], ux[3]);
-                st4(a.uy + o, uy[0], uy[1], uy[2], uy[3]);
+            for (int k = 0; k < 9; ++k) {
+                float t[V];
 #pragma unroll
-                for (int c = 0; c < kCellsPerThread; ++c) {
+                for (int c = 0; c < V; ++c) t[c] = g[c][k];
+                stv<V>(a.dst + k * plane + o, t);
+            }
+            if (EMIT) {
+                stv<V>(a.rho + o, rho);
+                stv<V>(a.ux + o, ux);
+                stv<V>(a.uy + o, uy);
+#pragma unroll
+                for (int c = 0; c < V; ++c) {
                     const float m2 = vmag2_strict(ux[c], uy[c]);
                     vnan |= (m2 != m2);
                     vmax = fmaxf(vmax, m2);
@@ -164,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
             }
         }
 
-        // ---- boundary ring (ref:438-450): scalar stores, after this thread's float4 stores -----
+        // ---- boundary ring (ref:438-450): scalar stores, after this thread's vector stores -----
         if (touches_ring) {
             const int fc = *a.ctr_in + 1;
             const float ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
@@ -173,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
             sink.sm_mac = nullptr;
             sink.il0 = sink.j0 = sink.bx = sink.by = sink.row_hi = sink.col_lo = sink.col_hi = 0;
 #pragma unroll
-            for (int c = 0; c < kCellsPerThread; ++c) {
+            for (int c = 0; c < V; ++c) {
                 const int j = j0 + c;
                 if (j < 1 || j > ny - 2) continue;
                 if (!(j == 1 || j == ny - 2 || edge_col)) continue;

@@ -21,16 +21,28 @@ constexpr int kTileCells = kTileBX * kTileBY;
 constexpr int kInStages = 3;
 constexpr int kOutStages = 2;
 constexpr int kConsumerWarps = 16;
-constexpr int kTmaThreads = 32 * (1 + kConsumerWarps);
+constexpr int kConsumers = 32 * kConsumerWarps;
+constexpr int kTmaThreads = 32 * (2 + kConsumerWarps);   // + load-producer warp + store warp
 // TMA needs a 16-byte aligned start address, so the +-1 float shift of the pull in y cannot be put
 // into the box origin.  Planes with e_ky != 0 are fetched with a 4-float apron on both sides of the
 // tile rows (aligned origin j0 - 4, rows of BY + 8 floats) and read at offset 4 - e_ky; the shift in
 // x is a whole row of the tensor and goes into the box origin directly.
 constexpr int kHaloY = 4;
 constexpr int kRowHalo = kTileBY + 2 * kHaloY;
-__host__ __device__ constexpr int plane_row(int k) { return (k == 2 || k >= 4) ? kRowHalo : kTileBY; }   // e_ky != 0 for k = 2,4,5,6,7,8
-__host__ __device__ constexpr int plane_off(int k) { return k == 0 ? 0 : plane_off(k - 1) + plane_row(k - 1) * kTileBX; }  // floats
-constexpr int kCodeOff = plane_off(9) * 4;                            // byte offset of the cell-code tile
+// per-plane row length and float offset inside a stage (e_ky != 0 for k = 2, 4, 5, 6, 7, 8)
+constexpr int kRowN = kTileBY * kTileBX, kRowH = kRowHalo * kTileBX;
+__device__ constexpr int kPlaneRow[9] = {kTileBY, kTileBY, kRowHalo, kTileBY, kRowHalo, kRowHalo, kRowHalo, kRowHalo, kRowHalo};
+__device__ constexpr int kPlaneOff[10] = {0,
+                                          kRowN,
+                                          2 * kRowN,
+                                          2 * kRowN + kRowH,
+                                          3 * kRowN + kRowH,
+                                          3 * kRowN + 2 * kRowH,
+                                          3 * kRowN + 3 * kRowH,
+                                          3 * kRowN + 4 * kRowH,
+                                          3 * kRowN + 5 * kRowH,
+                                          3 * kRowN + 6 * kRowH};
+constexpr int kCodeOff = (3 * kRowN + 6 * kRowH) * 4;                 // byte offset of the cell-code tile
 constexpr int kStageInBytes = kCodeOff + kTileCells;                  // 9 fp32 planes + 1 byte cell codes
 constexpr int kStageInStride = (kStageInBytes + 127) / 128 * 128;
 constexpr int kStageOutBytes = 12 * kTileCells * 4;                   // 9 f planes + rho, ux, uy
@@ -100,16 +112,13 @@ __device__ __forceinline__ void tma_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_bar() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-}
 
 // Tensor maps (all fp32 except the cell codes), built on the host by lbm2d_capi.cu:
 //   map_src : 3-D (pitch, nx_local, 9) over the source buffer, box (BY, BX, 1)      (planes with e_ky == 0)
 //   map_srch: same tensor, box (BY + 8, BX, 1)                                       (planes with e_ky != 0)
 //   map_code: 2-D (pitch, nx_local) uint8, box (BY, BX)
-//   map_dst : 3-D (row_hi, col_hi - col_lo, 9) over the destination buffer starting at column col_lo
-//   map_mac : 3-D (row_hi, col_hi - col_lo, 3) over the rho / ux / uy planes (EMIT)
+//   map_dst : 3-D (row_hi, col_hi - col_lo, 9) over the destination buffer starting at column col_lo, box (BY, BX, 9)
+//   map_mac : 3-D (row_hi, col_hi - col_lo, 3) over the rho / ux / uy planes (EMIT), box (BY, BX, 3)
 template <bool STRICT, bool EMIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_srch,
@@ -123,10 +132,15 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     uint64_t *full = bars, *empty = bars + kInStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *ofull = bars + 2 * kInStages, *oempty = ofull + kOutStages;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kInStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kConsumerWarps);
+        }
+        for (int o = 0; o < kOutStages; ++o) {
+            mbar_init(&ofull[o], kConsumerWarps);
+            mbar_init(&oempty[o], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (blockIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
@@ -134,7 +148,7 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     __syncthreads();
 
     if (warp == 0) {
-        // ===================== producer: TMA loads of the shifted planes =========================
+        // ===================== load producer: TMA loads of the shifted planes =====================
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
@@ -146,101 +160,130 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
                 mbar_expect_tx(&full[s], kStageInBytes);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    if (kEy[k] == 0) tma_load_3d(st + plane_off(k) * 4, &map_src, j0, il0 - kEx[k], k, &full[s]);
-                    else tma_load_3d(st + plane_off(k) * 4, &map_srch, j0 - kHaloY, il0 - kEx[k], k, &full[s]);
+                    if (kEy[k] == 0) tma_load_3d(st + kPlaneOff[k] * 4, &map_src, j0, il0 - kEx[k], k, &full[s]);
+                    else tma_load_3d(st + kPlaneOff[k] * 4, &map_srch, j0 - kHaloY, il0 - kEx[k], k, &full[s]);
                 }
                 tma_load_2d(st + kCodeOff, &map_code, j0, il0, &full[s]);
             }
         }
         return;
     }
+    if (warp == 1) {
+        // ===================== store warp: one TMA store per finished output tile ==================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+                const int o = it % kOutStages;
+                const uint32_t ph = (it / kOutStages) & 1;
+                const int sx = (t / a.n_ty) * kTileBX, j0 = (t % a.n_ty) * kTileBY;
+                const float *out = out_base + o * (kStageOutBytes / 4);
+                mbar_wait(&ofull[o], ph);
+                tma_store_3d(&map_dst, j0, sx, 0, out);                       // box (BY, BX, 9): all planes at once
+                if (EMIT) tma_store_3d(&map_mac, j0, sx, 0, out + 9 * kTileCells);  // box (BY, BX, 3)
+                tma_commit();
+                tma_wait_read<0>();   // shared memory of this stage has been read: consumers may refill it
+                mbar_arrive(&oempty[o]);
+            }
+            tma_wait_all<0>();        // every store of this CTA has landed before the grid ends
+        }
+        return;
+    }
 
     // ========================= consumers: collide from smem, write the output tile ===============
-    const int ctid = threadIdx.x - 32;  // 0 .. kConsumerWarps*32-1
+    const int ctid = threadIdx.x - 64;  // 0 .. kConsumers-1
     const int ny = a.ny;
+    constexpr int kIter = kTileCells / kConsumers;   // cells per thread per tile (2)
+    static_assert(kTileCells % kConsumers == 0 && kConsumers % kTileBY == 0, "tile / thread mapping");
+    const int y = ctid % kTileBY, xb = ctid / kTileBY;          // this thread's row is the same in every tile
     float vmax = 0.0f;
     int vnan = 0;
-    float ramp = 0.0f;
-    {
-        const int fc = *a.ctr_in + 1;
-        ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
-    }
+    const float ramp = __ldg(a.ramp_tab + min(*a.ctr_in + 1, a.warmup));
     int it = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
         const int s = it % kInStages;
         const uint32_t ph = (it / kInStages) & 1;
         const int o = it % kOutStages;
+        const uint32_t oph = (it / kOutStages) & 1;
         const int il0 = a.col_lo + (t / a.n_ty) * kTileBX, j0 = (t % a.n_ty) * kTileBY;
         const float *in = reinterpret_cast<const float *>(in_base + s * kStageInStride);
         const unsigned char *codes = in_base + s * kStageInStride + kCodeOff;
         float *out = out_base + o * (kStageOutBytes / 4);
+        const int j = j0 + y;
 
+        // sponge damping of this thread's cells (ref:364-380), fetched before waiting on the tile
+        float dmp[kIter];
+        {
+            const float dy = (j < ny) ? __ldg(a.damp_y + j) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) {
+                const int il = il0 + xb + i * (kConsumers / kTileBY);
+                dmp[i] = fmaxf((il < a.nx_local) ? __ldg(a.damp_x + il) : 0.0f, dy);
+            }
+        }
         TileSink sink;
         sink.sm_f = out;
         sink.sm_mac = out + 9 * kTileCells;
         sink.il0 = il0; sink.j0 = j0; sink.bx = kTileBX; sink.by = kTileBY;
         sink.row_hi = a.row_hi; sink.col_lo = a.col_lo; sink.col_hi = a.col_hi;
 
-        mbar_wait(&full[s], ph);
-#pragma unroll 1
-        for (int c = ctid; c < kTileCells; c += kConsumerWarps * 32) {
-            const int x = c / kTileBY, y = c % kTileBY;
-            const int il = il0 + x, j = j0 + y;
-            const bool interior = (il >= 1) && (il <= a.nx_local - 2) && (j >= 1) && (j <= ny - 2);
-            if (!interior) continue;  // ring cells are written by their owners, the rest is clipped by the store
-            float fin[9], g[9];
+        mbar_wait(&full[s], ph);          // the tile's shifted planes have landed
+        mbar_wait(&oempty[o], oph ^ 1);   // the output stage is no longer being read by an earlier store
+
+        float fin[kIter][9], g[kIter][9], rho[kIter], ux[kIter], uy[kIter];
+        bool interior[kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const int x = xb + i * (kConsumers / kTileBY);
+            const int il = il0 + x;
+            interior[i] = (il >= 1) && (il <= a.nx_local - 2) && (j >= 1) && (j <= ny - 2);
 #pragma unroll
             for (int k = 0; k < 9; ++k)
-                fin[k] = in[plane_off(k) + x * plane_row(k) + y + (kEy[k] == 0 ? 0 : kHaloY - kEy[k])];
-            const float damp = fmaxf(__ldg(a.damp_x + il), __ldg(a.damp_y + j));
-            if (STRICT) collide_strict(a.phys, fin, damp, g);
-            else collide_fast(a.phys, fin, damp, g);
-            float rho, ux, uy;
-            macro_from_f<STRICT>(g, rho, ux, uy);
+                fin[i][k] = in[kPlaneOff[k] + x * kPlaneRow[k] + y + (kEy[k] == 0 ? 0 : kHaloY - kEy[k])];
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            if (STRICT) collide_strict(a.phys, fin[i], dmp[i], g[i]);
+            else collide_fast(a.phys, fin[i], dmp[i], g[i]);
+            macro_from_f<STRICT>(g[i], rho[i], ux[i], uy[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            if (!interior[i]) continue;   // ring cells are written by their owners, the rest is clipped by the store
+            const int x = xb + i * (kConsumers / kTileBY);
+            const int il = il0 + x, c = x * kTileBY + y;
             const bool owner = (j == 1) || (j == ny - 2) || (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
             if (owner) {  // rare: produce the ring cells hanging off this cell from its un-refilled state
                 Cell me;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) me.f[k] = g[k];
-                me.rho = rho; me.ux = ux; me.uy = uy;
+                for (int k = 0; k < 9; ++k) me.f[k] = g[i][k];
+                me.rho = rho[i]; me.ux = ux[i]; me.uy = uy[i];
                 ring_from_owner(a.ring, &sink, EMIT, il, j, &me, ramp, &vmax, &vnan);
             }
             if (codes[c] & 1) {  // obstacle refill, ref:452-455
-                ux = 0.0f; uy = 0.0f;
+                ux[i] = 0.0f; uy[i] = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) g[k] = __fmul_rn(kW[k], rho);
+                for (int k = 0; k < 9; ++k) g[i][k] = __fmul_rn(kW[k], rho[i]);
             }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) out[k * kTileCells + c] = g[k];
+            for (int k = 0; k < 9; ++k) out[k * kTileCells + c] = g[i][k];
             if (EMIT) {
-                out[9 * kTileCells + c] = rho;
-                out[10 * kTileCells + c] = ux;
-                out[11 * kTileCells + c] = uy;
-                const float m2 = vmag2_strict(ux, uy);
+                out[9 * kTileCells + c] = rho[i];
+                out[10 * kTileCells + c] = ux[i];
+                out[11 * kTileCells + c] = uy[i];
+                const float m2 = vmag2_strict(ux[i], uy[i]);
                 vnan |= (m2 != m2);
                 vmax = fmaxf(vmax, m2);
             }
         }
-        // input stage consumed: hand it back to the producer (one arrival per consumer warp)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        // output tile complete: make the generic-proxy writes visible to TMA, then one thread stores
+        // hand the input stage back to the producer and the output tile to the store warp: the writes
+        // above go through the generic proxy, TMA reads through the async proxy -> fence, then arrive
         fence_async_smem();
-        consumer_bar();
-        if (ctid == 0) {
-            const int sx = il0 - a.col_lo;  // store-tensor column coordinate
-#pragma unroll
-            for (int k = 0; k < 9; ++k) tma_store_3d(&map_dst, j0, sx, k, out + k * kTileCells);
-            if (EMIT) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) tma_store_3d(&map_mac, j0, sx, k, out + (9 + k) * kTileCells);
-            }
-            tma_commit();
-            tma_wait_read<kOutStages - 1>();  // the OTHER output stage is free again
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&ofull[o]);
         }
-        consumer_bar();
     }
-    if (ctid == 0) tma_wait_all<0>();  // all stores of this CTA have landed before the grid ends
 
     if (EMIT) {
         for (int sft = 16; sft > 0; sft >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));

@@ -49,7 +49,9 @@ typedef enum {
 typedef enum {
     LBM_KERNEL_AUTO = 0,     /* TMA variant on grids large enough to fill the GPU, register variant otherwise */
     LBM_KERNEL_REGISTER = 1, /* one warp per 128-cell column segment, float4 loads + warp shuffles */
-    LBM_KERNEL_TMA = 2       /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
+    LBM_KERNEL_TMA = 2,      /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
+    LBM_KERNEL_REGISTER2 = 3, /* register variant, 2 cells per thread (64-bit accesses, higher occupancy) */
+    LBM_KERNEL_REGISTER1 = 4  /* register variant, 1 cell per thread */
 } LbmKernel;
 
 typedef enum {
