@@ -306,7 +306,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     s->ny = p.ny;
     s->pitch = round_up(p.ny, 32);
     s->plane = (long long)s->nx_local * s->pitch;
-    s->vwidth = (p.kernel == LBM_KERNEL_REGISTER2) ? 2 : (p.kernel == LBM_KERNEL_REGISTER1 ? 1 : 4);
+    // AUTO -> the 2-cells-per-thread register variant (fastest measured: profiles/)
+    s->vwidth = (p.kernel == LBM_KERNEL_REGISTER) ? 4 : (p.kernel == LBM_KERNEL_REGISTER1 ? 1 : 2);
     s->nseg = (s->pitch + 32 * s->vwidth - 1) / (32 * s->vwidth);
     s->n_items = (s->nx_local - 2) * s->nseg;
 
@@ -430,7 +431,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         const long long tiles = ((long long)s->nx_local + lbm::kTileBX - 1) / lbm::kTileBX * ((s->ny + lbm::kTileBY - 1) / lbm::kTileBY);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        s->use_tma = p.kernel == LBM_KERNEL_TMA || (p.kernel == LBM_KERNEL_AUTO && tiles >= 4LL * sms);
+        (void)tiles;
+        s->use_tma = p.kernel == LBM_KERNEL_TMA;
         if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_REGISTER1) {
             delete s;
             return fail(LBM_ERR_INVALID, "unsupported kernel variant");
@@ -469,7 +471,8 @@ int lbm_run(LbmHandle h, int steps) {
     if (int rc = check_handle(h, true)) return rc;
     if (steps < 0) return fail(LBM_ERR_INVALID, "steps < 0");
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
-    const int blocks = (h->n_items + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+    const int ncols = h->nx_local - 2;
+    const dim3 blocks((h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock, std::min(ncols, 65535), (ncols + 65534) / 65535);
     for (int it = 0; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));

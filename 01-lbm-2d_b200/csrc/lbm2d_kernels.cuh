@@ -71,12 +71,13 @@ __device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) 
 // with scalar stores after the vector stores.
 template <bool STRICT, bool EMIT, int V>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 2 : (V == 2 ? 4 : 6))) step_kernel(const StepArgs a) {
+    // grid: x = blocks of 8 segments down a column, y (+ z beyond 65535) = interior column
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
-    if (item >= a.n_items) return;                                          // warp-uniform
-    const int il = 1 + item / a.nseg;                                        // local column
-    const int j0 = (item % a.nseg) * (32 * V) + lane * V;
+    const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int il = 1 + blockIdx.y + blockIdx.z * 65535;                      // local column
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
+    if (seg >= a.nseg || il > a.nx_local - 2) return;                       // warp-uniform
+    const int j0 = seg * (32 * V) + lane * V;
     const bool lane_on = j0 < a.pitch;
     const int ny = a.ny, pitch = a.pitch;
     const long long plane = a.plane;
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 2 : (V == 2 ? 4 : 6))) ste
     int vnan = 0;
     if (live) {
         // ---- collide + macro (ref:266-436) --------------------------------------------------
+        // rho / u of a cell are only consumed by EMIT steps, the obstacle refill and ring owners
+        const bool edge_col = (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
+        const bool touches_ring = (j0 <= 1) || (j0 + V >= ny - 1) || edge_col;
         float g[V][9];
         float rho[V], ux[V], uy[V];
 #pragma unroll
@@ -138,12 +142,11 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 2 : (V == 2 ? 4 : 6))) ste
             const float damp = fmaxf(dx, dy[c]);
             if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
             else collide_fast(a.phys, fin[c], damp, g[c]);
-            macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+            rho[c] = ux[c] = uy[c] = 0.0f;
+            if (EMIT || touches_ring || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
         }
 
         // ---- owners of ring cells keep a copy of their fresh un-refilled state (rare) ---------
-        const bool edge_col = (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
-        const bool touches_ring = (j0 <= 1) || (j0 + V >= ny - 1) || edge_col;
         Cell own[V];
         if (touches_ring) {
 #pragma unroll

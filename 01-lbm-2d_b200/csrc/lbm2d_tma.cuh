@@ -244,7 +244,11 @@ step_tma_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         for (int i = 0; i < kIter; ++i) {
             if (STRICT) collide_strict(a.phys, fin[i], dmp[i], g[i]);
             else collide_fast(a.phys, fin[i], dmp[i], g[i]);
-            macro_from_f<STRICT>(g[i], rho[i], ux[i], uy[i]);
+            const int x = xb + i * (kConsumers / kTileBY);
+            const int il = il0 + x;
+            const bool owner = (j == 1) || (j == ny - 2) || (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
+            rho[i] = ux[i] = uy[i] = 0.0f;
+            if (EMIT || owner || (codes[x * kTileBY + y] & 1)) macro_from_f<STRICT>(g[i], rho[i], ux[i], uy[i]);
         }
 #pragma unroll
         for (int i = 0; i < kIter; ++i) {

@@ -47,7 +47,7 @@ typedef enum {
 } LbmArith;
 
 typedef enum {
-    LBM_KERNEL_AUTO = 0,     /* TMA variant on grids large enough to fill the GPU, register variant otherwise */
+    LBM_KERNEL_AUTO = 0,     /* the fastest measured variant (currently REGISTER2) */
     LBM_KERNEL_REGISTER = 1, /* one warp per 128-cell column segment, float4 loads + warp shuffles */
     LBM_KERNEL_TMA = 2,      /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
     LBM_KERNEL_REGISTER2 = 3, /* register variant, 2 cells per thread (64-bit accesses, higher occupancy) */
