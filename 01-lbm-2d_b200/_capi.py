@@ -64,8 +64,8 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if build_if_missing and _build.needs_build():
+    path = os.environ.get("LBM2D_LIB", _build.LIB_PATH)  # LBM2D_LIB: experiment builds (tuning sweeps)
+    if path == _build.LIB_PATH and build_if_missing and _build.needs_build():
         _build.build_library()
     if not os.path.exists(path):
         raise LbmError(f"{path} is missing: build it with __graft_entry__.build() (no CPU fallback exists)")

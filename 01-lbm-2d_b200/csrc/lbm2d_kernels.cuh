@@ -8,7 +8,22 @@
 
 namespace lbm {
 
-constexpr int kWarpsPerBlock = 8;
+// Tuning knobs (measured on B200, 8192x2048: profiles/r01_tuning_sweep.md).  Small CTAs win: the
+// warps of a CTA move through load / math / store in lock-step, so many small CTAs per SM keep the
+// memory pipeline evenly fed.
+#ifndef LBM_WPB
+#define LBM_WPB 2
+#endif
+#ifndef LBM_MINB2
+#define LBM_MINB2 16
+#endif
+#ifndef LBM_MINB1
+#define LBM_MINB1 24
+#endif
+#ifndef LBM_STCS
+#define LBM_STCS 0
+#endif
+constexpr int kWarpsPerBlock = LBM_WPB;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
 struct StepArgs {
@@ -49,9 +64,15 @@ __device__ __forceinline__ void ldv(const float *p, float (&o)[V]) {
 }
 template <int V>
 __device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
+#if LBM_STCS
+    if (V == 4) __stcs(reinterpret_cast<float4 *>(p), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
+    else if (V == 2) __stcs(reinterpret_cast<float2 *>(p), make_float2(o[0], o[1 % V]));
+    else __stcs(p, o[0]);
+#else
     if (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
     else if (V == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1 % V]);
     else *p = o[0];
+#endif
 }
 template <int V>
 __device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) {
@@ -70,7 +91,7 @@ __device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) 
 // cells are produced by the thread that owns their interior neighbour (ring_from_owner) and written
 // with scalar stores after the vector stores.
 template <bool STRICT, bool EMIT, int V>
-__global__ void __launch_bounds__(kThreads, (V == 4 ? 2 : (V == 2 ? 4 : 6))) step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
     // grid: x = blocks of 8 segments down a column, y (+ z beyond 65535) = interior column
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
