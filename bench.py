@@ -48,17 +48,25 @@ def measured_hbm_peak():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark(self, which):
+        """wall-clock bounds of the timed region (samples are filtered to it)"""
+        if which == 0:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -67,7 +75,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")][1:]))
 
     def stop(self):
         if not self.proc:
@@ -75,7 +83,11 @@ class ClockSampler:
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 - 0.02 <= t <= (self.t1 or t) + 0.05)]
+        where = "timed region"
+        if not rows:  # the timed region was shorter than nvidia-smi's sampling period
+            rows, where = [r for (_, r) in self.rows], "warm-up + timed region"
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -85,7 +97,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled_over": where}
 
 
 def build_workload(name, n_gpus):
@@ -195,17 +207,20 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: exactly K steps between two events on the solver's stream
-    solver.run_step(max(3, args.warmup))
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up so that it samples the timed region
+    solver.run_step(max(3, args.warmup))
+    barrier()
     l0 = solver.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark(0)
     e0.record(stream)
     solver.run_step(args.steps)
     e1.record(stream)
     barrier()
+    sampler.mark(1)
     ms = e0.elapsed_time(e1)
     launches = solver.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
@@ -250,6 +265,14 @@ def run_ours(args):
     achieved = ALGO_BYTES_PER_CELL * cells_per_gpu / avg_kernel_s / 1e9
     cpu_mlups, cores, cpu_n, cpu_dt = (time_cpu_port(*build_workload(args.workload, 1), budget_s=15.0)
                                        if world == 1 and not args.quick else (None, None, None, None))
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this grid
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["grid"] == [int(nx // world), int(ny)] and args.arith == "fast" and args.kernel == "auto":
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -265,7 +288,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "lbm::step_kernel<false,false>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "lbm::step_kernel<STRICT=false, EMIT=false, V=2> (K-1 of K launches; the K-th is the EMIT variant)",
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_per_gpu},
     }
     if cpu_mlups is not None:
