@@ -29,6 +29,7 @@ class LbmDeviceView(C.Structure):
     ]
 
 
+COMM_ID_BYTES = 128
 ARITH = {"fast": 0, "strict": 1}
 KERNEL = {"auto": 0, "register": 1, "tma": 2, "register2": 3, "register1": 4}
 EXPORTS = {
@@ -48,6 +49,8 @@ EXPORTS = {
     "lbm_get_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_moments": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_f": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),
     "lbm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }

@@ -3,6 +3,8 @@
 // kernels of lbm2d_kernels.cuh.  No CPU fallback: every path below needs a CUDA device.
 #include "../../include/lbm2d.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,8 +35,47 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+// ---- NCCL, resolved at run time from the library torch has already loaded (no link-time dependency) ----
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;
+typedef void *Comm;
+enum { kFloat32 = 7 };
+struct Api {
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*Send)(const void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+inline Api &api() {
+    static Api a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return a;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    a.Send = (decltype(a.Send))dlsym(lib, "ncclSend");
+    a.Recv = (decltype(a.Recv))dlsym(lib, "ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(lib, "ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd;
+    return a;
+}
+}  // namespace nccl
+
 struct LbmSolver {
     LbmParams p{};
+    nccl::Comm comm = nullptr;
+    int rank = 0, nranks = 1;
     int device = 0;
     cudaStream_t stream = nullptr;
     int nx_local = 0, ny = 0, pitch = 0, nseg = 0, n_items = 0;
@@ -68,6 +109,7 @@ struct LbmSolver {
 
     ~LbmSolver() {
         cudaSetDevice(device);
+        if (comm) nccl::api().CommDestroy(comm);
         for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging})
@@ -246,6 +288,40 @@ lbm::ExportArgs make_export_args(const LbmSolver *s) {
     a.strict = s->p.arith == LBM_ARITH_STRICT;
     a.phys = s->phys;
     return a;
+}
+
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        int r__ = (expr);                                                                           \
+        if (r__ != 0) {                                                                             \
+            const char *m__ = nccl::api().GetErrorString ? nccl::api().GetErrorString(r__) : "?";   \
+            return fail(LBM_ERR_NCCL, std::string(#expr) + ": " + m__);                             \
+        }                                                                                           \
+    } while (0)
+
+// One halo column per interface: the populations that stream across it.  `buf` is the
+// buffer the step just wrote; sends read the first / last OWNED column, receives fill the halo columns.
+int exchange_halos(LbmSolver *s, float *buf) {
+    if (!s->comm || s->nranks == 1) return LBM_OK;
+    nccl::Api &n = nccl::api();
+    static const int east_going[3] = {1, 5, 8}, west_going[3] = {3, 6, 7};
+    const size_t cnt = (size_t)s->pitch;
+    const long long pl = s->plane;
+    NCCL_TRY(n.GroupStart());
+    if (!s->east_ring) {  // east neighbour = rank + 1
+        for (int q = 0; q < 3; ++q) {
+            NCCL_TRY(n.Send(buf + east_going[q] * pl + (long long)(s->nx_local - 2) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, s->stream));
+            NCCL_TRY(n.Recv(buf + west_going[q] * pl + (long long)(s->nx_local - 1) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, s->stream));
+        }
+    }
+    if (!s->west_ring) {  // west neighbour = rank - 1
+        for (int q = 0; q < 3; ++q) {
+            NCCL_TRY(n.Send(buf + west_going[q] * pl + (long long)s->pitch, cnt, nccl::kFloat32, s->rank - 1, s->comm, s->stream));
+            NCCL_TRY(n.Recv(buf + east_going[q] * pl, cnt, nccl::kFloat32, s->rank - 1, s->comm, s->stream));
+        }
+    }
+    NCCL_TRY(n.GroupEnd());
+    return LBM_OK;
 }
 
 int check_handle(LbmHandle h, bool need_init) {
@@ -447,6 +523,31 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     return LBM_OK;
 }
 
+int lbm_comm_unique_id(uint8_t out[LBM_COMM_ID_BYTES]) {
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    nccl::Api &n = nccl::api();
+    if (!n.ok) return fail(LBM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    nccl::UniqueId id;
+    NCCL_TRY(n.GetUniqueId(&id));
+    std::memcpy(out, id.internal, LBM_COMM_ID_BYTES);
+    return LBM_OK;
+}
+
+int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id_bytes[LBM_COMM_ID_BYTES]) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return fail(LBM_ERR_INVALID, "bad rank / nranks / id");
+    if ((rank == 0) != h->west_ring || (rank == nranks - 1) != h->east_ring)
+        return fail(LBM_ERR_INVALID, "slabs must be ordered west to east by rank and tile the global domain");
+    nccl::Api &n = nccl::api();
+    if (!n.ok) return fail(LBM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    nccl::UniqueId id;
+    std::memcpy(id.internal, id_bytes, LBM_COMM_ID_BYTES);
+    NCCL_TRY(n.CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank;
+    h->nranks = nranks;
+    return LBM_OK;
+}
+
 int lbm_destroy(LbmHandle h) {
     if (!h) return LBM_OK;
     cudaSetDevice(h->device);
@@ -494,6 +595,7 @@ int lbm_run(LbmHandle h, int steps) {
             }
             h->steps_done++;
             h->launches++;
+            if (int rc = exchange_halos(h, h->f[par ^ 1])) return rc;
             continue;
         }
         const lbm::StepArgs a = make_args(h);
@@ -510,6 +612,7 @@ int lbm_run(LbmHandle h, int steps) {
 #undef LBM_LAUNCH_REG
         h->steps_done++;
         h->launches++;
+        if (int rc = exchange_halos(h, a.dst)) return rc;
     }
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;

@@ -124,6 +124,17 @@ int lbm_get_moments(LbmHandle h, float *out_nxny9);
 /* f_old.to_numpy() (which = 0) / f_new.to_numpy() (which = 1): (nx,ny,9).  Parity / debugging. */
 int lbm_get_f(LbmHandle h, int which, float *out_nxny9);
 
+/* ---- multi-GPU x-slabs: one process per GPU, one handle per slab ---------------
+ * Every rank creates its handle with nx_global / slab_x0 set (slabs in rank order, west to east), then all
+ * ranks call lbm_comm_connect() collectively with the id rank 0 obtained from lbm_comm_unique_id() (moved
+ * between processes by the host, e.g. torch.distributed broadcast).  From then on lbm_run() exchanges one
+ * halo column per interface and step over NCCL (NVLink): the three populations that cross it in each
+ * direction (f1,f5,f8 eastward, f3,f6,f7 westward), ny floats each.  Global force / max|u| are reduced by
+ * the host (they are per-batch scalars). */
+#define LBM_COMM_ID_BYTES 128
+int lbm_comm_unique_id(uint8_t out[LBM_COMM_ID_BYTES]);
+int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id[LBM_COMM_ID_BYTES]);
+
 /* ---- HBM-resident access (no host copies): device pointers valid until lbm_destroy ---------- */
 typedef struct {
     float *f_cur;      /* 9 planes, plane stride `plane_stride` floats, (nx_local, pitch) y fastest */

@@ -89,7 +89,11 @@ def ramp_value(frame_count: int, warmup_steps, F=np.float32):
 class OracleLBM:
     """Same surface as the reference class (ref:10), state held in numpy arrays."""
 
-    def __init__(self, config, mask_data=None, dtype=np.float32, exact_inv_m=False):
+    def __init__(self, config, mask_data=None, dtype=np.float32, exact_inv_m=False, slab=None):
+        """`slab=(x0, nx_owned)`: hold only global columns [x0, x0+nx_owned) plus one halo column on every
+        side that is not a domain boundary; `halo_pack` / `halo_unpack` move the populations that
+        cross an interface.  A set of slab oracles exchanging halos every step equals the monolithic oracle
+        bit for bit (tests/test_slab_cpu.py) -- that is the property the multi-GPU path relies on."""
         self.config = config
         self.F = F = np.dtype(dtype).type
         sim = config["simulation"]  # ref:33-44 (strict indexing: KeyError on missing keys)
@@ -117,13 +121,21 @@ class OracleLBM:
         self.sponge_w_bot = max(1, zones["sponge_bot"])
         self.sponge_strength = zones["sponge_strength"]
 
-        nx, ny = self.nx, self.ny  # ref:97-128
+        # slab geometry: local column il <-> global column il + self._lo
+        x0, nx_owned = (0, self.nx) if slab is None else (int(slab[0]), int(slab[1]))
+        self.west_ring, self.east_ring = x0 == 0, x0 + nx_owned == self.nx
+        self._own0 = 0 if self.west_ring else 1
+        self._nx_owned = nx_owned
+        self._lo = x0 - self._own0
+        self.nx_local = nx_owned + (0 if self.west_ring else 1) + (0 if self.east_ring else 1)
+        nxg = self.nx
+        nx, ny = self.nx_local, self.ny  # ref:97-128
         self.rho = np.zeros((nx, ny), F)
         self.vel = np.zeros((nx, ny, 2), F)
         self.f_old = np.zeros((nx, ny, 9), F)
         self.f_new = np.zeros((nx, ny, 9), F)
         if mask_data is not None:
-            self.mask = np.asarray(mask_data).astype(np.float32).reshape(nx, ny)
+            self.mask = np.asarray(mask_data).astype(np.float32).reshape(nxg, ny)[self._lo:self._lo + nx].copy()
         else:
             self.mask = np.zeros((nx, ny), np.float32)
         bc = config["boundary_condition"]
@@ -147,13 +159,14 @@ class OracleLBM:
         self.damp_x = np.zeros(nx, F)
         self.damp_y = np.zeros(ny, F)
         st = F(self.sponge_strength)
-        for i in range(nx):
-            if i > (nx - self.sponge_w_out):
-                c = F(i - (nx - self.sponge_w_out)) / F(self.sponge_w_out)
-                self.damp_x[i] = st * (c * c)
+        for il in range(nx):
+            i = il + self._lo  # the sponge uses the GLOBAL x
+            if i > (nxg - self.sponge_w_out):
+                c = F(i - (nxg - self.sponge_w_out)) / F(self.sponge_w_out)
+                self.damp_x[il] = st * (c * c)
             elif i < self.sponge_w_in:
                 c = F(self.sponge_w_in - i) / F(self.sponge_w_in)
-                self.damp_x[i] = st * (c * c)
+                self.damp_x[il] = st * (c * c)
         for j in range(ny):
             if j < self.sponge_w_bot:
                 c = F(self.sponge_w_bot - j) / F(self.sponge_w_bot)
@@ -188,7 +201,7 @@ class OracleLBM:
     def collide_and_stream(self):
         """ref:243-420 (interior cells, solids included)."""
         F = self.F
-        nx, ny = self.nx, self.ny
+        nx, ny = self.nx_local, self.ny
         fo = self.f_old
         f = [fo[1 - E[k, 0] : nx - 1 - E[k, 0], 1 - E[k, 1] : ny - 1 - E[k, 1], k] for k in range(9)]
         with np.errstate(all="ignore"):
@@ -239,7 +252,7 @@ class OracleLBM:
     def update_macro_var(self):
         """ref:422-436"""
         F = self.F
-        nx, ny = self.nx, self.ny
+        nx, ny = self.nx_local, self.ny
         fn = self.f_new[1 : nx - 1, 1 : ny - 1]
         self.f_old[1 : nx - 1, 1 : ny - 1] = fn
         rho = np.zeros(fn.shape[:2], F)
@@ -266,7 +279,7 @@ class OracleLBM:
         jnb = np.asarray(jnb)
         with np.errstate(all="ignore"):
             if t == 0:
-                west = ibc == 0
+                west = (ibc + self._lo) == 0
                 if west.any():  # ref:461-486
                     ib, jb, in_, jn = ibc[west], jbc[west], inb[west], jnb[west]
                     rho_in = F(self.rho_in_target)
@@ -297,7 +310,7 @@ class OracleLBM:
                         + self.f_old[in_, jn]
                     )
             elif t == 1:
-                east = ibc == self.nx - 1
+                east = (ibc + self._lo) == self.nx - 1
                 if east.any():  # ref:495-527
                     ib, jb, in_, jn = ibc[east], jbc[east], inb[east], jnb[east]
                     rho_out = F(self.rho_out_target)
@@ -345,20 +358,43 @@ class OracleLBM:
     def apply_bc(self):
         """ref:438-455"""
         F = self.F
-        nx, ny = self.nx, self.ny
+        nx, ny = self.nx_local, self.ny
         self.frame_count += 1
         ramp = ramp_value(self.frame_count, self.warmup_steps, F)
         j = np.arange(1, ny - 1)
         z = np.zeros_like(j)
-        self._apply_bc_core(0, z, j, z + 1, j, ramp)
-        self._apply_bc_core(2, z + (nx - 1), j, z + (nx - 2), j, ramp)
-        i = np.arange(nx)
+        if self.west_ring:
+            self._apply_bc_core(0, z, j, z + 1, j, ramp)
+        if self.east_ring:
+            self._apply_bc_core(2, z + (nx - 1), j, z + (nx - 2), j, ramp)
+        i = np.arange(self._own0, self._own0 + self._nx_owned)  # owned columns (all of them when not a slab)
         z = np.zeros_like(i)
         self._apply_bc_core(1, i, z + (ny - 1), i, z + (ny - 2), ramp)
         self._apply_bc_core(3, i, z, i, z + 1, ramp)
         solid = self.mask == 1.0
+        solid[: self._own0] = False                       # halo columns belong to the neighbour
+        solid[self._own0 + self._nx_owned:] = False
         self.vel[solid] = 0
         self.f_old[solid] = self._f_eq(self.rho[solid], self.vel[solid])
+
+    # ------------------------------------------------------------------ slab halos
+    EAST_GOING = (1, 5, 8)   # populations with e_x = +1: pulled from column i-1
+    WEST_GOING = (3, 6, 7)
+
+    def halo_pack(self, side):
+        """Populations of the first ('W') / last ('E') owned column that stream into the neighbour."""
+        if side == "E":
+            return self.f_old[self._own0 + self._nx_owned - 1][:, list(self.EAST_GOING)].copy()
+        return self.f_old[self._own0][:, list(self.WEST_GOING)].copy()
+
+    def halo_unpack(self, side, data):
+        """Fill the 'W' / 'E' halo column with what the neighbour packed for us.  The halo's f_new (read
+        by the force of an owned solid next to it) equals f_old at interior rows, as on the owning rank."""
+        col = self.nx_local - 1 if side == "E" else 0
+        planes = list(self.WEST_GOING if side == "E" else self.EAST_GOING)
+        self.f_old[col][:, planes] = data
+        fn = self.f_new[col]
+        fn[1:-1, planes] = data[1:-1]
 
     def run_step(self, steps=1):
         """ref:552-573"""
@@ -371,14 +407,16 @@ class OracleLBM:
     def get_force(self):
         """ref:588-646; terms added sequentially in (i, j, k) order."""
         F = self.F
-        nx, ny = self.nx, self.ny
+        nx, ny = self.nx_local, self.ny
         terms_x, terms_y = [], []
         solid_idx = np.argwhere(self.mask == 1)
         for i, j in solid_idx:
+            if not (self._own0 <= i < self._own0 + self._nx_owned):
+                continue
             for k in range(9):
                 dx, dy, inv_k, fx, fy = FORCE_LUT[k]
                 ni, nj = i + dx, j + dy
-                if 0 <= ni < nx and 0 <= nj < ny and self.mask[ni, nj] == 0:
+                if 0 <= ni + self._lo < self.nx and 0 <= nj < ny and self.mask[ni, nj] == 0:
                     fv = F(2.0) * self.f_new[ni, nj, inv_k]
                     terms_x.append(fv * F(fx))
                     terms_y.append(fv * F(fy))
