@@ -21,6 +21,11 @@ class LbmParams(C.Structure):
     ]
 
 
+class LbmExportConfig(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("x1", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
+                ("target_w", C.c_int32), ("target_h", C.c_int32)]
+
+
 class LbmDeviceView(C.Structure):
     _fields_ = [
         ("f_cur", C.c_void_p), ("f_prev", C.c_void_p), ("rho", C.c_void_p), ("ux", C.c_void_p), ("uy", C.c_void_p),
@@ -49,6 +54,9 @@ EXPORTS = {
     "lbm_get_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_moments": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_f": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "lbm_export_configure": (C.c_int, [C.c_void_p, C.POINTER(LbmExportConfig)]),
+    "lbm_export_frame": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lbm_export_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),

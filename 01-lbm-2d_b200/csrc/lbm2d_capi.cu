@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "lbm2d_export.cuh"
 #include "lbm2d_tma.cuh"
 
 namespace {
@@ -96,6 +97,14 @@ struct LbmSolver {
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
     lbm::TmaArgs tma_args{};
+    // export reduction state (lbm_export_*)
+    bool exp_ready = false;
+    lbm::ExportGeom exp_geom{};
+    lbm::AreaEntry *exp_xtab = nullptr, *exp_ytab = nullptr;
+    int *exp_xoff = nullptr, *exp_yoff = nullptr;
+    float *exp_tmp = nullptr, *exp_frame = nullptr;
+    double *exp_sum = nullptr, *exp_velsq = nullptr, *exp_vor = nullptr, *exp_minmax = nullptr;
+    int64_t exp_count = 0;
     lbm::Link *links = nullptr;
     int n_links = 0;
     double *force_partial = nullptr;
@@ -112,7 +121,9 @@ struct LbmSolver {
         if (comm) nccl::api().CommDestroy(comm);
         for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
-                          (void *)force_partial, (void *)force_out, (void *)staging})
+                          (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
+                          (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
+                          (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax})
             if (ptr) cudaFree(ptr);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -711,6 +722,112 @@ int lbm_get_moments(LbmHandle h, float *out) { return export9(h, 0, out); }
 int lbm_get_f(LbmHandle h, int which, float *out) {
     if (which != 0 && which != 1) return fail(LBM_ERR_INVALID, "which must be 0 (f_old) or 1 (f_new)");
     return export9(h, which == 0 ? 1 : 2, out);
+}
+
+// computeResizeAreaTab of OpenCV's resize.cpp (see oracle/writer_oracle.py::area_tab), grouped by destination
+static double area_tab(int ssize, int dsize, std::vector<lbm::AreaEntry> &tab, std::vector<int> &off) {
+    const double inv = (double)dsize / (double)ssize, scale = 1.0 / inv;
+    tab.clear();
+    off.assign(dsize + 1, 0);
+    for (int dx = 0; dx < dsize; ++dx) {
+        off[dx] = (int)tab.size();
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1);
+        sx1 = std::min(sx1, sx2);
+        if (sx1 - fsx1 > 1e-3) tab.push_back({sx1 - 1, (float)((sx1 - fsx1) / cell)});
+        for (int sx = sx1; sx < sx2; ++sx) tab.push_back({sx, (float)(1.0 / cell)});
+        if (fsx2 - sx2 > 1e-3) tab.push_back({sx2, (float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell)});
+    }
+    off[dsize] = (int)tab.size();
+    return scale;
+}
+
+int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!cfg) return fail(LBM_ERR_INVALID, "cfg is null");
+    if (h->p.nx != h->p.nx_global) return fail(LBM_ERR_INVALID, "export reduction is implemented for single-GPU handles");
+    const int cw = cfg->x1 - cfg->x0, ch = cfg->y1 - cfg->y0;
+    if (cfg->x0 < 0 || cfg->y0 < 0 || cfg->x1 > h->p.nx || cfg->y1 > h->ny || cw <= 0 || ch <= 0)
+        return fail(LBM_ERR_INVALID, "export ROI outside the grid or empty");
+    if (cfg->target_w < 1 || cfg->target_h < 1 || cfg->target_w > cw || cfg->target_h > ch)
+        return fail(LBM_ERR_INVALID, "INTER_AREA export supports shrinking only (1 <= target <= crop)");
+    for (void *ptr : {(void *)h->exp_xtab, (void *)h->exp_ytab, (void *)h->exp_xoff, (void *)h->exp_yoff, (void *)h->exp_tmp,
+                      (void *)h->exp_frame, (void *)h->exp_sum, (void *)h->exp_velsq, (void *)h->exp_vor, (void *)h->exp_minmax})
+        if (ptr) cudaFree(ptr);
+    h->exp_xtab = h->exp_ytab = nullptr;
+    h->exp_xoff = h->exp_yoff = nullptr;
+    h->exp_tmp = h->exp_frame = nullptr;
+    h->exp_sum = h->exp_velsq = h->exp_vor = h->exp_minmax = nullptr;
+    h->exp_ready = false;
+
+    lbm::ExportGeom &g = h->exp_geom;
+    g.x0 = cfg->x0; g.y0 = cfg->y0; g.cw = cw; g.ch = ch; g.tw = cfg->target_w; g.th = cfg->target_h;
+    std::vector<lbm::AreaEntry> xt, yt;
+    std::vector<int> xo, yo;
+    const double sx = area_tab(cw, g.tw, xt, xo), sy = area_tab(ch, g.th, yt, yo);
+    g.ix = (int)std::lrint(sx);
+    g.iy = (int)std::lrint(sy);
+    g.fast = std::fabs(sx - g.ix) < 2.220446049250313e-16 && std::fabs(sy - g.iy) < 2.220446049250313e-16;
+    const size_t npx = (size_t)g.tw * g.th;
+    CUDA_TRY(cudaMalloc(&h->exp_xtab, xt.size() * sizeof(lbm::AreaEntry)));
+    CUDA_TRY(cudaMalloc(&h->exp_ytab, yt.size() * sizeof(lbm::AreaEntry)));
+    CUDA_TRY(cudaMalloc(&h->exp_xoff, xo.size() * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->exp_yoff, yo.size() * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->exp_tmp, (size_t)9 * cw * ch * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->exp_frame, 9 * npx * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->exp_sum, 9 * npx * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->exp_velsq, npx * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->exp_vor, npx * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->exp_minmax, 18 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->exp_xtab, xt.data(), xt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->exp_ytab, yt.data(), yt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->exp_xoff, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->exp_yoff, yo.data(), yo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(h->exp_sum, 0, 9 * npx * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->exp_velsq, 0, npx * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->exp_vor, 0, npx * sizeof(double)));
+    double mm[18];
+    for (int c = 0; c < 9; ++c) { mm[c] = INFINITY; mm[9 + c] = -INFINITY; }
+    CUDA_TRY(cudaMemcpy(h->exp_minmax, mm, sizeof(mm), cudaMemcpyHostToDevice));
+    h->exp_count = 0;
+    h->exp_ready = true;
+    return LBM_OK;
+}
+
+int lbm_export_frame(LbmHandle h, float *out_chw) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
+    const lbm::ExportGeom g = h->exp_geom;
+    const lbm::ExportArgs a = make_export_args(h);
+    const size_t npx = (size_t)g.tw * g.th;
+    lbm::roi_moments_kernel<<<dim3((g.ch + 127) / 128, g.cw), 128, 0, h->stream>>>(a, g, h->exp_tmp);
+    const dim3 rgrid((g.th + 63) / 64, g.tw, 9);
+    if (g.fast) lbm::area_fast_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_frame);
+    else lbm::area_resize_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_xtab, h->exp_xoff, h->exp_ytab, h->exp_yoff, h->exp_frame);
+    lbm::export_stats_kernel<<<dim3((g.tw + 127) / 128, g.th), 128, 0, h->stream>>>(h->exp_frame, g.tw, g.th, h->exp_sum, h->exp_velsq, h->exp_vor);
+    lbm::export_minmax_kernel<<<9, 256, 0, h->stream>>>(h->exp_frame, (long long)npx, h->exp_minmax, h->exp_minmax + 9);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 4;
+    h->exp_count++;
+    if (out_chw) CUDA_TRY(cudaMemcpyAsync(out_chw, h->exp_frame, 9 * npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw, double *abs_vor_sum_hw, double *min9,
+                     double *max9, int64_t *count) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
+    const size_t npx = (size_t)h->exp_geom.tw * h->exp_geom.th;
+    if (running_sum_chw) CUDA_TRY(cudaMemcpyAsync(running_sum_chw, h->exp_sum, 9 * npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (vel_sq_sum_hw) CUDA_TRY(cudaMemcpyAsync(vel_sq_sum_hw, h->exp_velsq, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (abs_vor_sum_hw) CUDA_TRY(cudaMemcpyAsync(abs_vor_sum_hw, h->exp_vor, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (min9) CUDA_TRY(cudaMemcpyAsync(min9, h->exp_minmax, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (max9) CUDA_TRY(cudaMemcpyAsync(max9, h->exp_minmax + 9, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (count) *count = h->exp_count;
+    return LBM_OK;
 }
 
 int lbm_device_view(LbmHandle h, LbmDeviceView *out) {

@@ -1,0 +1,151 @@
+// On-device export reduction: what the reference's HDF5 writer does on the
+// host with the full (nx, ny, 9) moments frame -- ROI crop, per-channel cv2.INTER_AREA down-sampling
+// and the running statistics of io/lbm_writer.py:135-210 (cited as writer:LINE) -- done on the GPU so that
+// only the (9, H, W) export frame crosses PCIe (604 MB -> ~11 MB per frame at 8192x2048).
+//
+// The resize restates OpenCV's INTER_AREA for single-channel float32 shrinking operation for operation
+// (strict fp32, same summation order: see oracle/writer_oracle.py, which is tested bit-for-bit against
+// cv2), one thread per output pixel walking its slice of the x / y area tables.
+#pragma once
+#include "lbm2d_kernels.cuh"
+
+namespace lbm {
+
+struct AreaEntry {
+    int si;       // source index
+    float alpha;  // weight (float, as OpenCV's DecimateAlpha)
+};
+
+struct ExportGeom {
+    int x0, y0, cw, ch;  // ROI origin (local column, row) and size
+    int tw, th;          // target size
+    int fast;            // both scales integer: resizeAreaFast_ path
+    int ix, iy;          // integer scales (fast path)
+};
+
+// 9 moments of the reference's f_new over the ROI -> tmp[c][x][y] (y fastest)
+__global__ void roi_moments_kernel(const ExportArgs a, ExportGeom g, float *__restrict__ tmp) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = blockIdx.y;
+    if (y >= g.ch) return;
+    float f[9], m[9];
+    load_f_new(a, g.x0 + x, g.y0 + y, f);
+    moments_strict(f, m);
+    const long long n = (long long)g.cw * g.ch, o = (long long)x * g.ch + y;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tmp[k * n + o] = m[k];
+}
+
+// ResizeArea_Invoker: out[c][dy][dx] = sum_j beta_j * (sum_k alpha_k * S[sy_j][sx_k]), every product
+// and sum individually rounded, in table order.
+__global__ void area_resize_kernel(const float *__restrict__ tmp, ExportGeom g, const AreaEntry *__restrict__ xtab,
+                                   const int *__restrict__ xoff, const AreaEntry *__restrict__ ytab,
+                                   const int *__restrict__ yoff, float *__restrict__ out) {
+    const int dy = blockIdx.x * blockDim.x + threadIdx.x;  // lanes along y: neighbouring source rows
+    const int dx = blockIdx.y, c = blockIdx.z;
+    if (dy >= g.th) return;
+    const float *S = tmp + (long long)c * g.cw * g.ch;
+    float total = 0.0f;
+    const int k0 = xoff[dx], k1 = xoff[dx + 1];
+    for (int j = yoff[dy]; j < yoff[dy + 1]; ++j) {
+        const int sy = ytab[j].si;
+        float buf = 0.0f;
+        for (int k = k0; k < k1; ++k) buf = __fadd_rn(buf, __fmul_rn(S[(long long)xtab[k].si * g.ch + sy], xtab[k].alpha));
+        total = __fadd_rn(total, __fmul_rn(ytab[j].alpha, buf));
+    }
+    out[((long long)c * g.th + dy) * g.tw + dx] = total;
+}
+
+// resizeAreaFast_: integer scales.  2x2: ((a+b)+(c+d))*0.25 (the SIMD kernel); otherwise the scalar loop
+// unrolled by four the way OpenCV writes it, times 1/area.
+__global__ void area_fast_kernel(const float *__restrict__ tmp, ExportGeom g, float *__restrict__ out) {
+    const int dy = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dx = blockIdx.y, c = blockIdx.z;
+    if (dy >= g.th) return;
+    const float *S = tmp + (long long)c * g.cw * g.ch;
+    auto at = [&](int sy, int sx) { return S[(long long)sx * g.ch + sy]; };
+    float r;
+    if (g.ix == 2 && g.iy == 2) {
+        const float a = at(2 * dy, 2 * dx), b = at(2 * dy, 2 * dx + 1), cc = at(2 * dy + 1, 2 * dx), d = at(2 * dy + 1, 2 * dx + 1);
+        r = __fmul_rn(__fadd_rn(__fadd_rn(a, b), __fadd_rn(cc, d)), 0.25f);
+    } else {
+        const int area = g.ix * g.iy;
+        float sum = 0.0f;
+        int k = 0;
+        auto val = [&](int q) { return at(dy * g.iy + q / g.ix, dx * g.ix + q % g.ix); };
+        for (; k <= area - 4; k += 4)
+            sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(__fadd_rn(val(k), val(k + 1)), val(k + 2)), val(k + 3)));
+        for (; k < area; ++k) sum = __fadd_rn(sum, val(k));
+        r = __fmul_rn(sum, 1.0f / (float)area);
+    }
+    out[((long long)c * g.th + dy) * g.tw + dx] = r;
+}
+
+// writer:176-210: running sum of the frame (float64), sum of u^2+v^2, sum of |vorticity| on the
+// down-sampled grid (np.gradient: central differences inside, one-sided at the edges, float32).
+__global__ void export_stats_kernel(const float *__restrict__ frame, int tw, int th, double *__restrict__ running_sum,
+                                    double *__restrict__ vel_sq_sum, double *__restrict__ abs_vor_sum) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= tw) return;
+    const long long n = (long long)tw * th, o = (long long)y * tw + x;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) running_sum[c * n + o] += (double)frame[c * n + o];
+    auto uv = [&](int yy, int xx, float &u, float &v) {
+        const long long q = (long long)yy * tw + xx;
+        const float rs = fmaxf(frame[q], 1e-6f);
+        u = __fdiv_rn(frame[3 * n + q], rs);
+        v = __fdiv_rn(frame[5 * n + q], rs);
+    };
+    float u, v;
+    uv(y, x, u, v);
+    vel_sq_sum[o] += (double)__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v));
+    // dv/dx along W (axis 1), du/dy along H (axis 0)
+    float ua, va, ub, vb, dvdx = 0.0f, dudy = 0.0f;
+    if (tw > 1) {
+        const int xa = x == 0 ? 0 : x - 1, xb = x == tw - 1 ? tw - 1 : x + 1;
+        uv(y, xa, ua, va);
+        uv(y, xb, ub, vb);
+        dvdx = (x == 0 || x == tw - 1) ? __fsub_rn(vb, va) : __fdiv_rn(__fsub_rn(vb, va), 2.0f);
+    }
+    if (th > 1) {
+        const int ya = y == 0 ? 0 : y - 1, yb = y == th - 1 ? th - 1 : y + 1;
+        uv(ya, x, ua, va);
+        uv(yb, x, ub, vb);
+        dudy = (y == 0 || y == th - 1) ? __fsub_rn(ub, ua) : __fdiv_rn(__fsub_rn(ub, ua), 2.0f);
+    }
+    abs_vor_sum[o] += (double)fabsf(__fsub_rn(dvdx, dudy));
+}
+
+// per-channel min / max of the frame folded into the running global min / max (writer:181-184)
+__global__ void export_minmax_kernel(const float *__restrict__ frame, long long n, double *__restrict__ gmin, double *__restrict__ gmax) {
+    const int c = blockIdx.x;
+    float lo = INFINITY, hi = -INFINITY;
+    bool nan = false;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = frame[c * n + i];
+        nan |= (v != v);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    __shared__ float slo[32], shi[32];
+    __shared__ int snan;
+    if (threadIdx.x == 0) snan = 0;
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if (nan) atomicOr(&snan, 1);
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+        if (snan) { gmin[c] = NAN; gmax[c] = NAN; }   // np.minimum / np.maximum propagate NaN
+        else {
+            gmin[c] = fmin(gmin[c], (double)lo);
+            gmax[c] = fmax(gmax[c], (double)hi);
+        }
+    }
+}
+
+}  // namespace lbm

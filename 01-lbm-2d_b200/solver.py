@@ -153,6 +153,29 @@ class LBM2D_MRT_LES:
         """ref:739-741 -> fresh (nx,ny,9) f32 array owned by the caller (it is queued to the writer thread)"""
         return self._get("lbm_get_moments", (self._nx_owned, self.ny, 9))
 
+    # ------------------------------------------------------------------ on-device export reduction
+    def export_configure(self, x0, x1, y0, y1, target_w, target_h):
+        """ROI crop + INTER_AREA target of the reference writer (io/lbm_writer.py:37-58); resets the statistics."""
+        cfg = _capi.LbmExportConfig(int(x0), int(x1), int(y0), int(y1), int(target_w), int(target_h))
+        _capi.check(self._lib.lbm_export_configure(self._h, C.byref(cfg)))
+        self._export_shape = (9, int(target_h), int(target_w))
+
+    def export_frame(self, want_frame=True):
+        """One export frame (9, H, W): moments -> crop -> INTER_AREA on the GPU, statistics accumulated there."""
+        out = np.empty(self._export_shape, np.float32) if want_frame else None
+        _capi.check(self._lib.lbm_export_frame(self._h, out.ctypes.data_as(C.c_void_p) if want_frame else None))
+        return out
+
+    def export_stats(self):
+        """Running accumulators of io/lbm_writer.py:176-210 -> dict (float64 arrays) + count."""
+        c, h, w = self._export_shape
+        rs, vs, vo = np.empty((c, h, w)), np.empty((h, w)), np.empty((h, w))
+        mn, mx, cnt = np.empty(9), np.empty(9), C.c_int64()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _capi.check(self._lib.lbm_export_stats(self._h, p(rs), p(vs), p(vo), p(mn), p(mx), C.byref(cnt)))
+        return {"running_sum": rs, "running_vel_sq_sum": vs, "sum_abs_vor": vo, "global_min": mn, "global_max": mx,
+                "running_count": int(cnt.value)}
+
     # ------------------------------------------------------------------ extras
     def step_count(self) -> int:
         v = C.c_int64()

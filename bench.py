@@ -257,6 +257,9 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_mlups = nx * ny * done / e2e_s / 1e6
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_hbm_peak()

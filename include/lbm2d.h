@@ -124,6 +124,23 @@ int lbm_get_moments(LbmHandle h, float *out_nxny9);
 /* f_old.to_numpy() (which = 0) / f_new.to_numpy() (which = 1): (nx,ny,9).  Parity / debugging. */
 int lbm_get_f(LbmHandle h, int which, float *out_nxny9);
 
+/* ---- on-device export reduction: io/lbm_writer.py:135-251 of the reference -------------------------
+ * lbm_export_configure(): ROI [x0,x1) x [y0,y1) in grid cells (the writer's crop, lbm_writer.py:37-42) and the
+ * target size (target_w, target_h) it derives from save_resolution_height (lbm_writer.py:52-58); resets
+ * the running statistics.  lbm_export_frame(): the 9 moments of get_moments_numpy() over the ROI,
+ * down-sampled per channel exactly like cv2.resize(..., INTER_AREA) (lbm_writer.py:150-163), accumulated
+ * into the running sum / min / max / sum(u^2+v^2) / sum|vorticity| (lbm_writer.py:176-210) on the device;
+ * `out_chw` (9, target_h, target_w) fp32 receives the frame (may be NULL).  lbm_export_stats(): the
+ * accumulators for finalize() (lbm_writer.py:212-251); any pointer may be NULL.  Single-GPU handles only. */
+typedef struct {
+    int32_t x0, x1, y0, y1;
+    int32_t target_w, target_h;
+} LbmExportConfig;
+int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg);
+int lbm_export_frame(LbmHandle h, float *out_chw);
+int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw, double *abs_vor_sum_hw,
+                     double *min9, double *max9, int64_t *count);
+
 /* ---- multi-GPU x-slabs: one process per GPU, one handle per slab ---------------
  * Every rank creates its handle with nx_global / slab_x0 set (slabs in rank order, west to east), then all
  * ranks call lbm_comm_connect() collectively with the id rank 0 obtained from lbm_comm_unique_id() (moved
