@@ -77,6 +77,9 @@ struct LbmSolver {
     LbmParams p{};
     nccl::Comm comm = nullptr;
     int rank = 0, nranks = 1;
+    cudaStream_t stream_e = nullptr;   // edge columns + halo exchange, overlapped with the interior
+    cudaEvent_t ev_m = nullptr, ev_e = nullptr, ev_e_prev = nullptr, ev_x = nullptr;
+    bool ev_e_prev_valid = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     int nx_local = 0, ny = 0, pitch = 0, nseg = 0, n_items = 0;
@@ -119,6 +122,9 @@ struct LbmSolver {
     ~LbmSolver() {
         cudaSetDevice(device);
         if (comm) nccl::api().CommDestroy(comm);
+        for (cudaEvent_t ev : {ev_m, ev_e, ev_e_prev, ev_x})
+            if (ev) cudaEventDestroy(ev);
+        if (stream_e) cudaStreamDestroy(stream_e);
         for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
@@ -193,6 +199,10 @@ lbm::StepArgs make_args(const LbmSolver *s) {
     a.east_ring = s->east_ring;
     a.warmup = s->p.warmup_steps;
     a.ring = s->ring_ctx + (par ^ 1);
+    a.il0 = 1;
+    a.il_step = 1;
+    a.il_count = s->nx_local - 2;
+    a.bump_ctr = 1;
     a.phys = s->phys;
     return a;
 }
@@ -312,7 +322,7 @@ lbm::ExportArgs make_export_args(const LbmSolver *s) {
 
 // One halo column per interface: the populations that stream across it.  `buf` is the
 // buffer the step just wrote; sends read the first / last OWNED column, receives fill the halo columns.
-int exchange_halos(LbmSolver *s, float *buf) {
+int exchange_halos(LbmSolver *s, float *buf, cudaStream_t st) {
     if (!s->comm || s->nranks == 1) return LBM_OK;
     nccl::Api &n = nccl::api();
     static const int east_going[3] = {1, 5, 8}, west_going[3] = {3, 6, 7};
@@ -321,14 +331,14 @@ int exchange_halos(LbmSolver *s, float *buf) {
     NCCL_TRY(n.GroupStart());
     if (!s->east_ring) {  // east neighbour = rank + 1
         for (int q = 0; q < 3; ++q) {
-            NCCL_TRY(n.Send(buf + east_going[q] * pl + (long long)(s->nx_local - 2) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, s->stream));
-            NCCL_TRY(n.Recv(buf + west_going[q] * pl + (long long)(s->nx_local - 1) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, s->stream));
+            NCCL_TRY(n.Send(buf + east_going[q] * pl + (long long)(s->nx_local - 2) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, st));
+            NCCL_TRY(n.Recv(buf + west_going[q] * pl + (long long)(s->nx_local - 1) * s->pitch, cnt, nccl::kFloat32, s->rank + 1, s->comm, st));
         }
     }
     if (!s->west_ring) {  // west neighbour = rank - 1
         for (int q = 0; q < 3; ++q) {
-            NCCL_TRY(n.Send(buf + west_going[q] * pl + (long long)s->pitch, cnt, nccl::kFloat32, s->rank - 1, s->comm, s->stream));
-            NCCL_TRY(n.Recv(buf + east_going[q] * pl, cnt, nccl::kFloat32, s->rank - 1, s->comm, s->stream));
+            NCCL_TRY(n.Send(buf + west_going[q] * pl + (long long)s->pitch, cnt, nccl::kFloat32, s->rank - 1, s->comm, st));
+            NCCL_TRY(n.Recv(buf + east_going[q] * pl, cnt, nccl::kFloat32, s->rank - 1, s->comm, st));
         }
     }
     NCCL_TRY(n.GroupEnd());
@@ -556,6 +566,13 @@ int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id_bytes[L
     NCCL_TRY(n.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank;
     h->nranks = nranks;
+    if (nranks > 1 && !std::getenv("LBM2D_NO_OVERLAP")) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->stream_e, cudaStreamNonBlocking, hi));  // edge + comm first
+        for (cudaEvent_t *ev : {&h->ev_m, &h->ev_e, &h->ev_e_prev, &h->ev_x})
+            CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    }
     return LBM_OK;
 }
 
@@ -584,7 +601,11 @@ int lbm_run(LbmHandle h, int steps) {
     if (steps < 0) return fail(LBM_ERR_INVALID, "steps < 0");
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
     const int ncols = h->nx_local - 2;
-    const dim3 blocks((h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock, std::min(ncols, 65535), (ncols + 65534) / 65535);
+    const dim3 blocks_all((h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock, std::min(ncols, 65535), (ncols + 65534) / 65535);
+    if (h->comm && h->nranks > 1 && h->stream_e) {  // the side stream starts behind everything already queued
+        CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
+        h->ev_e_prev_valid = false;
+    }
     for (int it = 0; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
@@ -606,11 +627,41 @@ int lbm_run(LbmHandle h, int steps) {
             }
             h->steps_done++;
             h->launches++;
-            if (int rc = exchange_halos(h, h->f[par ^ 1])) return rc;
+            if (int rc = exchange_halos(h, h->f[par ^ 1], h->stream)) return rc;
             continue;
         }
-        const lbm::StepArgs a = make_args(h);
-#define LBM_LAUNCH_REG(S, E, V) lbm::step_kernel<S, E, V><<<blocks, lbm::kThreads, 0, h->stream>>>(a)
+        lbm::StepArgs a = make_args(h);
+        const bool overlap = h->comm && h->nranks > 1 && h->nx_local >= 6 && h->stream_e;
+        cudaStream_t st = h->stream;
+        dim3 blocks = blocks_all;
+        if (overlap) {
+            // Edge columns (1 and nx_local-2) first on the side stream, halo exchange right behind them, the
+            // interior on the main stream meanwhile.  edge(n) needs interior(n-1) and exchange(n-1);
+            // interior(n) needs edge(n-1) and interior(n-1); see DESIGN.md section 5 "slabs".
+            lbm::StepArgs e = a;
+            e.il0 = 1; e.il_step = h->nx_local - 3; e.il_count = 2; e.bump_ctr = 0;
+            if (emit) CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));  // orders the max|u| reset before the edge kernel
+            CUDA_TRY(cudaStreamWaitEvent(h->stream_e, h->ev_m, 0));
+            const dim3 eb(blocks_all.x, 2, 1);
+#define LBM_LAUNCH_EDGE(S, E, V) lbm::step_kernel<S, E, V><<<eb, lbm::kThreads, 0, h->stream_e>>>(e)
+#define LBM_LAUNCH_EV(V)                                                     \
+    do {                                                                    \
+        if (strict) { if (emit) LBM_LAUNCH_EDGE(true, true, V); else LBM_LAUNCH_EDGE(true, false, V); } \
+        else { if (emit) LBM_LAUNCH_EDGE(false, true, V); else LBM_LAUNCH_EDGE(false, false, V); }      \
+    } while (0)
+            if (h->vwidth == 4) LBM_LAUNCH_EV(4);
+            else if (h->vwidth == 2) LBM_LAUNCH_EV(2);
+            else LBM_LAUNCH_EV(1);
+#undef LBM_LAUNCH_EV
+#undef LBM_LAUNCH_EDGE
+            CUDA_TRY(cudaEventRecord(h->ev_e, h->stream_e));
+            if (int rc = exchange_halos(h, a.dst, h->stream_e)) return rc;
+            h->launches++;
+            a.il0 = 2; a.il_step = 1; a.il_count = h->nx_local - 4;
+            blocks = dim3(blocks_all.x, std::min(a.il_count, 65535), (a.il_count + 65534) / 65535);
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_e_prev_valid ? h->ev_e_prev : h->ev_e, 0));
+        }
+#define LBM_LAUNCH_REG(S, E, V) lbm::step_kernel<S, E, V><<<blocks, lbm::kThreads, 0, st>>>(a)
 #define LBM_LAUNCH_V(V)                                                     \
     do {                                                                    \
         if (strict) { if (emit) LBM_LAUNCH_REG(true, true, V); else LBM_LAUNCH_REG(true, false, V); } \
@@ -623,7 +674,15 @@ int lbm_run(LbmHandle h, int steps) {
 #undef LBM_LAUNCH_REG
         h->steps_done++;
         h->launches++;
-        if (int rc = exchange_halos(h, a.dst)) return rc;
+        if (overlap) {
+            CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
+            std::swap(h->ev_e, h->ev_e_prev);   // interior(n+1) waits on edge(n)
+            h->ev_e_prev_valid = true;
+        } else if (int rc = exchange_halos(h, a.dst, h->stream)) return rc;
+    }
+    if (h->comm && h->nranks > 1 && h->stream_e) {  // later work on the main stream sees the last exchange
+        CUDA_TRY(cudaEventRecord(h->ev_x, h->stream_e));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_x, 0));
     }
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;

@@ -42,6 +42,8 @@ struct StepArgs {
     int x_off;                      // global x of local column 0
     int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
     int warmup;
+    int il0, il_step, il_count;     // columns of this launch: il0 + blockIdx.y * il_step, blockIdx.y < il_count
+    int bump_ctr;                   // this launch advances frame_count (exactly one launch per step does)
     const RingCtx *ring;            // rare-path context in global memory (dst-specific)
     Physics phys;
 };
@@ -95,9 +97,10 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
     // grid: x = blocks of 8 segments down a column, y (+ z beyond 65535) = interior column
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int il = 1 + blockIdx.y + blockIdx.z * 65535;                      // local column
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
-    if (seg >= a.nseg || il > a.nx_local - 2) return;                       // warp-uniform
+    const int col = blockIdx.y + blockIdx.z * 65535;
+    const int il = a.il0 + col * a.il_step;                                  // local column
+    if (a.bump_ctr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
+    if (seg >= a.nseg || col >= a.il_count) return;                         // warp-uniform
     const int j0 = seg * (32 * V) + lane * V;
     const bool lane_on = j0 < a.pitch;
     const int ny = a.ny, pitch = a.pitch;
