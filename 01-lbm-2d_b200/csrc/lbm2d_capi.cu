@@ -77,6 +77,7 @@ struct LbmSolver {
     LbmParams p{};
     nccl::Comm comm = nullptr;
     int rank = 0, nranks = 1;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // 32 plain steps starting at parity 0 / 1 (launch-bound grids)
     cudaStream_t stream_e = nullptr;   // edge columns + halo exchange, overlapped with the interior
     cudaEvent_t ev_m = nullptr, ev_e = nullptr, ev_e_prev = nullptr, ev_x = nullptr;
     bool ev_e_prev_valid = false;
@@ -122,6 +123,8 @@ struct LbmSolver {
     ~LbmSolver() {
         cudaSetDevice(device);
         if (comm) nccl::api().CommDestroy(comm);
+        for (cudaGraphExec_t g : graph)
+            if (g) cudaGraphExecDestroy(g);
         for (cudaEvent_t ev : {ev_m, ev_e, ev_e_prev, ev_x})
             if (ev) cudaEventDestroy(ev);
         if (stream_e) cudaStreamDestroy(stream_e);
@@ -173,9 +176,9 @@ float ramp_at(int t, int warmup) {
     return 1.0f - c;
 }
 
-lbm::StepArgs make_args(const LbmSolver *s) {
+lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     lbm::StepArgs a{};
-    const int par = (int)(s->steps_done & 1);
+    const int par = par_override >= 0 ? par_override : (int)(s->steps_done & 1);
     a.src = s->f[par];
     a.dst = s->f[par ^ 1];
     a.code = s->code;
@@ -606,7 +609,33 @@ int lbm_run(LbmHandle h, int steps) {
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
     }
-    for (int it = 0; it < steps; ++it) {
+    // Launch-bound grids (a step of the L2-resident BASELINE configs is a few microseconds of GPU work): replay
+    // a captured CUDA graph of kGraphSteps plain steps; the tail and the EMIT step are launched directly.
+    constexpr int kGraphSteps = 32;
+    int done_by_graph = 0;
+    if (!h->comm && !h->use_tma && h->plane <= (1LL << 22) && steps - 1 >= kGraphSteps && !std::getenv("LBM2D_NO_GRAPH")) {
+        const int par0 = (int)(h->steps_done & 1);
+        if (!h->graph[par0]) {
+            cudaGraph_t g = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < kGraphSteps; ++i) {
+                const lbm::StepArgs a = make_args(h, (par0 + i) & 1);
+                if (h->vwidth == 4) { if (strict) lbm::step_kernel<true, false, 4><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 4><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
+                else if (h->vwidth == 2) { if (strict) lbm::step_kernel<true, false, 2><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 2><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
+                else { if (strict) lbm::step_kernel<true, false, 1><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 1><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
+            }
+            CUDA_TRY(cudaStreamEndCapture(h->stream, &g));
+            CUDA_TRY(cudaGraphInstantiate(&h->graph[par0], g, 0));
+            CUDA_TRY(cudaGraphDestroy(g));
+        }
+        while (steps - 1 - done_by_graph >= kGraphSteps) {
+            CUDA_TRY(cudaGraphLaunch(h->graph[par0], h->stream));
+            done_by_graph += kGraphSteps;
+            h->steps_done += kGraphSteps;   // even: the parity, and so the graph, stays the same
+            h->launches += kGraphSteps;
+        }
+    }
+    for (int it = done_by_graph; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
         if (h->use_tma) {
