@@ -58,6 +58,20 @@ __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
 }
 
 // aligned V-wide global accesses (V = 1, 2, 4 floats)
+#ifndef LBM_LDCS
+#define LBM_LDCS 0
+#endif
+#if LBM_LDCS
+#define LBM_LD(ptr) __ldcs(ptr)
+#else
+#define LBM_LD(ptr) __ldg(ptr)
+#endif
+template <int V>
+__device__ __forceinline__ void ldf(const float *p, float (&o)[V]) {   // populations: read exactly once per step
+    if (V == 4) { const float4 t = LBM_LD(reinterpret_cast<const float4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
+    else if (V == 2) { const float2 t = LBM_LD(reinterpret_cast<const float2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
+    else o[0] = LBM_LD(p);
+}
 template <int V>
 __device__ __forceinline__ void ldv(const float *p, float (&o)[V]) {
     if (V == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
 #pragma unroll
         for (int c = 0; c < V; ++c) v[k][c] = 0.f;
         edge[k] = 0.f;
-        if (lane_on) ldv<V>(col + j0, v[k]);
+        if (lane_on) ldf<V>(col + j0, v[k]);
         if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = __ldg(col + j0 - 1);
         if (kEy[k] == -1 && lane == 31 && j0 + V < ny) edge[k] = __ldg(col + j0 + V);
     }
