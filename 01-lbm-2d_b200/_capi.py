@@ -36,7 +36,7 @@ class LbmDeviceView(C.Structure):
 
 COMM_ID_BYTES = 128
 ARITH = {"fast": 0, "strict": 1}
-KERNEL = {"auto": 0, "register": 1, "tma": 2, "register2": 3, "register1": 4}
+KERNEL = {"auto": 0, "register": 1, "tma": 2, "register2": 3, "register1": 4, "async": 5}
 EXPORTS = {
     "lbm_abi_version": (C.c_int, []),
     "lbm_last_error": (C.c_char_p, []),

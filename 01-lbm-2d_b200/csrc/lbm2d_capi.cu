@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "lbm2d_async.cuh"
 #include "lbm2d_export.cuh"
 #include "lbm2d_tma.cuh"
 
@@ -98,6 +99,8 @@ struct LbmSolver {
     lbm::RingCtx *ring_ctx = nullptr;  // [2], one per destination buffer
     bool use_tma = false;
     int vwidth = 4;  // cells per thread of the register variant
+    bool use_async = false;
+    int async_grid = 0;
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
     lbm::TmaArgs tma_args{};
@@ -533,7 +536,18 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         (void)tiles;
         s->use_tma = p.kernel == LBM_KERNEL_TMA;
-        if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_REGISTER1) {
+        s->use_async = p.kernel == LBM_KERNEL_ASYNC;
+        if (s->use_async) {
+            const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
+            int per_sm = 0;
+            for (auto fnp : {(const void *)lbm::step_async_kernel<false, false>, (const void *)lbm::step_async_kernel<false, true>,
+                             (const void *)lbm::step_async_kernel<true, false>, (const void *)lbm::step_async_kernel<true, true>})
+                cudaFuncSetAttribute(fnp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::step_async_kernel<false, false>, 32 * lbm::kAWarps, smem);
+            if (std::getenv("LBM2D_ASYNC_CTAS")) per_sm = std::min(per_sm, std::atoi(std::getenv("LBM2D_ASYNC_CTAS")));
+            s->async_grid = std::max(1, per_sm) * sms;
+        }
+        if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_ASYNC) {
             delete s;
             return fail(LBM_ERR_INVALID, "unsupported kernel variant");
         }
@@ -613,7 +627,7 @@ int lbm_run(LbmHandle h, int steps) {
     // a captured CUDA graph of kGraphSteps plain steps; the tail and the EMIT step are launched directly.
     constexpr int kGraphSteps = 32;
     int done_by_graph = 0;
-    if (!h->comm && !h->use_tma && h->plane <= (1LL << 22) && steps - 1 >= kGraphSteps && !std::getenv("LBM2D_NO_GRAPH")) {
+    if (!h->comm && !h->use_tma && !h->use_async && h->plane <= (1LL << 22) && steps - 1 >= kGraphSteps && !std::getenv("LBM2D_NO_GRAPH")) {
         const int par0 = (int)(h->steps_done & 1);
         if (!h->graph[par0]) {
             cudaGraph_t g = nullptr;
@@ -690,6 +704,13 @@ int lbm_run(LbmHandle h, int steps) {
             blocks = dim3(blocks_all.x, std::min(a.il_count, 65535), (a.il_count + 65534) / 65535);
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_e_prev_valid ? h->ev_e_prev : h->ev_e, 0));
         }
+        if (h->use_async) {
+            const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
+            const int nseg64 = (h->pitch + lbm::kASeg - 1) / lbm::kASeg;
+            const int grid = std::min(h->async_grid, (a.il_count * nseg64 + lbm::kAWarps - 1) / lbm::kAWarps);
+            if (strict) { if (emit) lbm::step_async_kernel<true, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<true, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
+            else { if (emit) lbm::step_async_kernel<false, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<false, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
+        } else {
 #define LBM_LAUNCH_REG(S, E, V) lbm::step_kernel<S, E, V><<<blocks, lbm::kThreads, 0, st>>>(a)
 #define LBM_LAUNCH_V(V)                                                     \
     do {                                                                    \
@@ -701,6 +722,7 @@ int lbm_run(LbmHandle h, int steps) {
         else LBM_LAUNCH_V(1);
 #undef LBM_LAUNCH_V
 #undef LBM_LAUNCH_REG
+        }
         h->steps_done++;
         h->launches++;
         if (overlap) {

@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank"])
     ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e / cpu_baseline legs")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma", "register2", "register1"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma", "register2", "register1", "async"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

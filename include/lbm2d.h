@@ -51,7 +51,8 @@ typedef enum {
     LBM_KERNEL_REGISTER = 1, /* one warp per 128-cell column segment, float4 loads + warp shuffles */
     LBM_KERNEL_TMA = 2,      /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
     LBM_KERNEL_REGISTER2 = 3, /* register variant, 2 cells per thread (64-bit accesses, higher occupancy) */
-    LBM_KERNEL_REGISTER1 = 4  /* register variant, 1 cell per thread */
+    LBM_KERNEL_REGISTER1 = 4, /* register variant, 1 cell per thread */
+    LBM_KERNEL_ASYNC = 5      /* persistent warps with private cp.async shared-memory rings (prefetch 2 segments ahead) */
 } LbmKernel;
 
 typedef enum {

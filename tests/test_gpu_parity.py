@@ -72,7 +72,7 @@ def _assert_close(s, ref, ref64, tol=TOL, tag=""):
 
 
 # ------------------------------------------------------------------ golden vectors (reference under shim)
-KERNELS = ("register", "tma", "register2", "register1")
+KERNELS = ("register", "tma", "register2", "register1", "async")
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
