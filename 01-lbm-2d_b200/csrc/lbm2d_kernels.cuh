@@ -178,8 +178,13 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
 #pragma unroll
         for (int c = 0; c < V; ++c) {
             const float damp = fmaxf(dx, dy[c]);
+#ifdef LBM_NOMATH   // experiment: pure streaming bound of this access pattern
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[c][k] = fin[c][k] + damp;
+#else
             if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
             else collide_fast(a.phys, fin[c], damp, g[c]);
+#endif
             rho[c] = ux[c] = uy[c] = 0.0f;
             if (EMIT || touches_ring || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
         }
