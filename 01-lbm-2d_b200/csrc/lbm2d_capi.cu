@@ -209,6 +209,7 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.il_step = 1;
     a.il_count = s->nx_local - 2;
     a.bump_ctr = 1;
+    a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, s->nx_local, s->ny, a.west_ring, a.east_ring);
     a.phys = s->phys;
     return a;
 }
@@ -618,7 +619,17 @@ int lbm_run(LbmHandle h, int steps) {
     if (steps < 0) return fail(LBM_ERR_INVALID, "steps < 0");
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
     const int ncols = h->nx_local - 2;
-    const dim3 blocks_all((h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock, std::min(ncols, 65535), (ncols + 65534) / 65535);
+    // grid of the register variant: x = segment blocks of a column, y (z) = columns followed by the ring rows
+    auto grid_for = [&](lbm::StepArgs &a) {
+        const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+        a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, h->nx_local, h->ny, a.west_ring, a.east_ring);
+        const int ring_ctas = (a.n_ring + 32 * lbm::kWarpsPerBlock - 1) / (32 * lbm::kWarpsPerBlock);
+        const int rows = a.il_count + (ring_ctas + gx - 1) / gx;
+        return dim3(gx, std::min(rows, 65535), (rows + 65534) / 65535);
+    };
+    lbm::StepArgs a_all = make_args(h);
+    const dim3 blocks_all = grid_for(a_all);
+    (void)ncols;
     if (h->comm && h->nranks > 1 && h->stream_e) {  // the side stream starts behind everything already queued
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
@@ -685,7 +696,7 @@ int lbm_run(LbmHandle h, int steps) {
             e.il0 = 1; e.il_step = h->nx_local - 3; e.il_count = 2; e.bump_ctr = 0;
             if (emit) CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));  // orders the max|u| reset before the edge kernel
             CUDA_TRY(cudaStreamWaitEvent(h->stream_e, h->ev_m, 0));
-            const dim3 eb(blocks_all.x, 2, 1);
+            const dim3 eb = grid_for(e);
 #define LBM_LAUNCH_EDGE(S, E, V) lbm::step_kernel<S, E, V><<<eb, lbm::kThreads, 0, h->stream_e>>>(e)
 #define LBM_LAUNCH_EV(V)                                                     \
     do {                                                                    \
@@ -701,7 +712,7 @@ int lbm_run(LbmHandle h, int steps) {
             if (int rc = exchange_halos(h, a.dst, h->stream_e)) return rc;
             h->launches++;
             a.il0 = 2; a.il_step = 1; a.il_count = h->nx_local - 4;
-            blocks = dim3(blocks_all.x, std::min(a.il_count, 65535), (a.il_count + 65534) / 65535);
+            blocks = grid_for(a);
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_e_prev_valid ? h->ev_e_prev : h->ev_e, 0));
         }
         if (h->use_async) {

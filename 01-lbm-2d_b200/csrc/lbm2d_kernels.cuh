@@ -44,6 +44,7 @@ struct StepArgs {
     int warmup;
     int il0, il_step, il_count;     // columns of this launch: il0 + blockIdx.y * il_step, blockIdx.y < il_count
     int bump_ctr;                   // this launch advances frame_count (exactly one launch per step does)
+    int n_ring;                     // ring cells handled by this launch's ring warps
     const RingCtx *ring;            // rare-path context in global memory (dst-specific)
     Physics phys;
 };
@@ -58,10 +59,13 @@ __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
 }
 
 // aligned V-wide global accesses (V = 1, 2, 4 floats)
+// Population loads bypass L1 (ld.global.cg): every value is read exactly once per step; measured 1 % faster.
 #ifndef LBM_LDCS
-#define LBM_LDCS 0
+#define LBM_LDCS 2
 #endif
-#if LBM_LDCS
+#if LBM_LDCS == 2
+#define LBM_LD(ptr) __ldcg(ptr)
+#elif LBM_LDCS
 #define LBM_LD(ptr) __ldcs(ptr)
 #else
 #define LBM_LD(ptr) __ldg(ptr)
@@ -97,167 +101,216 @@ __device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) 
     else o[0] = __ldg(p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ring warps.  Every boundary-ring cell is a function of ONE adjacent interior cell's fresh, un-refilled
+// state (corners chain through the W/E cell).  Instead of making the interior thread that
+// owns that neighbour produce it (a serial, divergent detour for one lane of a streaming warp), extra
+// warps of the SAME launch take one ring cell per lane: they re-derive the owner's collision from the
+// source buffer (a handful of scalar loads; the ring is O(perimeter)) and run the reference's
+// apply_bc_core on it, 32 ring cells in parallel.  They depend on nothing the interior warps write.
+//
+// Enumeration of the ring cells of a launch covering columns {il0 + c * il_step, c < il_count}:
+//   [0, n)        top row    (il_c, ny-1)   <- owner (il_c, ny-2)      dr = 1      ref:449
+//   [n, 2n)       bottom row (il_c, 0)      <- owner (il_c, 1)         dr = 3      ref:450
+//   then, if the launch holds column 1 and that side is a domain boundary:
+//   W column (0, j), j = 1..ny-2 <- owner (1, j), dr = 0 (ref:446); corners (0, ny-1), (0, 0) <- W cell <- owner
+//   and likewise E column / corners for column nx_local-2 (dr = 2, ref:447).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int ring_cell_count(int il0, int il_step, int il_count, int nx_local, int ny, int west_ring, int east_ring) {
+    const bool w = west_ring && il0 == 1;
+    const bool e = east_ring && (il0 + (il_count - 1) * il_step == nx_local - 2);
+    return 2 * il_count + (w ? ny : 0) + (e ? ny : 0);   // (ny - 2) column cells + 2 corners per side
+}
+
+template <bool STRICT, bool EMIT>
+__device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_fc, float &vmax, int &vnan) {
+    const int ny = a.ny, pitch = a.pitch, n = a.il_count;
+    const long long plane = a.plane;
+    // decode: ring cell (ilr, jr), its owner (ilo, jo), boundary side dr; corners chain W/E -> top/bottom
+    int ilr, jr, ilo, jo, dr, corner_dr = -1;
+    if (idx < 2 * n) {
+        const bool top = idx < n;
+        ilo = ilr = a.il0 + (top ? idx : idx - n) * a.il_step;
+        jo = top ? ny - 2 : 1;
+        jr = top ? ny - 1 : 0;
+        dr = top ? 1 : 3;
+    } else {
+        int q = idx - 2 * n;
+        const bool has_w = a.west_ring && a.il0 == 1;
+        const bool west = has_w && q < ny;
+        if (!west && has_w) q -= ny;
+        ilo = west ? 1 : a.nx_local - 2;
+        ilr = west ? 0 : a.nx_local - 1;
+        dr = west ? 0 : 2;
+        if (q < ny - 2) { jo = jr = q + 1; }
+        else if (q == ny - 2) { jo = ny - 2; jr = ny - 1; corner_dr = 1; }   // top corner through (ilr, ny-2)
+        else { jo = 1; jr = 0; corner_dr = 3; }                               // bottom corner through (ilr, 1)
+    }
+    // owner's pull + collision + macroscopic values (same arithmetic as the interior warps)
+    float fin[9], g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fin[k] = LBM_LD(a.src + k * plane + (long long)(ilo - kEx[k]) * pitch + (jo - kEy[k]));
+    const float damp = fmaxf(__ldg(a.damp_x + ilo), __ldg(a.damp_y + jo));
+    if (STRICT) collide_strict(a.phys, fin, damp, g);
+    else collide_fast(a.phys, fin, damp, g);
+    Cell me, r;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) me.f[k] = g[k];
+    macro_from_f<STRICT>(g, me.rho, me.ux, me.uy);
+    const float ramp = __ldg(a.ramp_tab + min(ramp_fc, a.warmup));
+    const int igo = a.x_off + ilo, igr = a.x_off + ilr;
+    cell_rest(r);
+    bc_core(a.phys, dr, igr, igo, me, r, ramp);
+    if (corner_dr >= 0) {   // ref:448-450 run over i = 0 and nx-1 too: the corner reads the W/E cell just produced
+        Cell cr;
+        cell_rest(cr);
+        bc_core(a.phys, corner_dr, igr, igr, r, cr, ramp);
+        r = cr;
+    }
+    const long long o = (long long)ilr * pitch + jr;
+    if (__ldg(a.code + o) & 1) refill(r);   // ref:452-455 also resets solid ring cells
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.dst[k * plane + o] = r.f[k];
+    if (EMIT) {
+        a.rho[o] = r.rho;
+        a.ux[o] = r.ux;
+        a.uy[o] = r.uy;
+        const float m2 = __fadd_rn(__fmul_rn(r.ux, r.ux), __fmul_rn(r.uy, r.uy));
+        vnan |= (m2 != m2);
+        vmax = fmaxf(vmax, m2);
+    }
+}
+
 // One fused pass: pull-stream, MRT-LES collision, sponge, macroscopic update, boundary ring,
 // obstacle refill (ref:552-573 = collide_and_stream + update_macro_var + apply_bc), f_src -> f_dst.
 //
-// "Register" variant.  Work decomposition: one warp = one (32 V)-cell segment of one interior column;
-// one thread = V consecutive cells in y (V = 4: 128-bit accesses).  Every access is aligned and fully
-// coalesced; the +-1 shift of the pull in y comes from the neighbouring lane by warp shuffle, with
-// one extra scalar load at each end of the segment (issued up front with the vector loads).  Ring
-// cells are produced by the thread that owns their interior neighbour (ring_from_owner) and written
-// with scalar stores after the vector stores.
+// "Register" variant.  Interior warps: one warp = one (32 V)-cell segment of one interior column, one
+// thread = V consecutive cells in y; every access is aligned and fully coalesced, the +-1 shift of the
+// pull in y comes from the neighbouring lane by warp shuffle with one extra scalar load at each end of
+// the segment, all issued before first use; no boundary code at all.  Ring warps (blockIdx.y beyond
+// the columns): one ring cell per lane, see above.
 template <bool STRICT, bool EMIT, int V>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
-    // grid: x = blocks of 8 segments down a column, y (+ z beyond 65535) = interior column
+    // grid: x = blocks of segments down a column, y (+ z beyond 65535) = interior column, then ring rows
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int col = blockIdx.y + blockIdx.z * 65535;
-    const int il = a.il0 + col * a.il_step;                                  // local column
     if (a.bump_ctr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
-    if (seg >= a.nseg || col >= a.il_count) return;                         // warp-uniform
-    const int j0 = seg * (32 * V) + lane * V;
-    const bool lane_on = j0 < a.pitch;
-    const int ny = a.ny, pitch = a.pitch;
-    const long long plane = a.plane;
-
-    // ---- pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky) -----------------------
-    // phase 1: every load of this thread is issued before the first use
-    float v[9][V];
-    float edge[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float *col = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
-#pragma unroll
-        for (int c = 0; c < V; ++c) v[k][c] = 0.f;
-        edge[k] = 0.f;
-        if (lane_on) ldf<V>(col + j0, v[k]);
-        if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = __ldg(col + j0 - 1);
-        if (kEy[k] == -1 && lane == 31 && j0 + V < ny) edge[k] = __ldg(col + j0 + V);
-    }
-    const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
-    float dx = 0.f;
-    float dy[V];
-    unsigned char code[V];
-#pragma unroll
-    for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; }
-    if (live) {
-        dx = __ldg(a.damp_x + il);
-        ldv<V>(a.damp_y + j0, dy);
-        ldcode<V>(a.code + (long long)il * pitch + j0, code);
-    }
-    // phase 2: assemble the shifted rows
-    float fin[V][9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        if (kEy[k] == 0) {
-#pragma unroll
-            for (int c = 0; c < V; ++c) fin[c][k] = v[k][c];
-        } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
-            float below = __shfl_up_sync(0xffffffffu, v[k][V - 1], 1);
-            if (lane == 0) below = edge[k];
-            fin[0][k] = below;
-#pragma unroll
-            for (int c = 1; c < V; ++c) fin[c][k] = v[k][c - 1];
-        } else {                   // needs j+1: first element of the lane above
-            float above = __shfl_down_sync(0xffffffffu, v[k][0], 1);
-            if (lane == 31) above = edge[k];
-#pragma unroll
-            for (int c = 0; c < V - 1; ++c) fin[c][k] = v[k][c + 1];
-            fin[V - 1][k] = above;
-        }
-    }
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
-    if (live) {
-        // ---- collide + macro (ref:266-436) --------------------------------------------------
-        // rho / u of a cell are only consumed by EMIT steps, the obstacle refill and ring owners
-        const bool edge_col = (il == 1 && a.west_ring) || (il == a.nx_local - 2 && a.east_ring);
-        const bool touches_ring = (j0 <= 1) || (j0 + V >= ny - 1) || edge_col;
-        float g[V][9];
-        float rho[V], ux[V], uy[V];
-#pragma unroll
-        for (int c = 0; c < V; ++c) {
-            const float damp = fmaxf(dx, dy[c]);
-#ifdef LBM_NOMATH   // experiment: pure streaming bound of this access pattern
-#pragma unroll
-            for (int k = 0; k < 9; ++k) g[c][k] = fin[c][k] + damp;
-#else
-            if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
-            else collide_fast(a.phys, fin[c], damp, g[c]);
-#endif
-            rho[c] = ux[c] = uy[c] = 0.0f;
-            if (EMIT || touches_ring || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
-        }
+    if (col >= a.il_count) {
+        // ------------------------------- ring warps ------------------------------------------
+        const int idx = ((col - a.il_count) * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT>(a, idx, *a.ctr_in + 1, vmax, vnan);
+    } else if (seg < a.nseg) {
+        // ------------------------------- interior warps --------------------------------------
+        const int il = a.il0 + col * a.il_step;                              // local column
+        const int j0 = seg * (32 * V) + lane * V;
+        const bool lane_on = j0 < a.pitch;
+        const int ny = a.ny, pitch = a.pitch;
+        const long long plane = a.plane;
 
-        // ---- owners of ring cells keep a copy of their fresh un-refilled state (rare) ---------
-        Cell own[V];
-        if (touches_ring) {
+        // pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky); every load issued before the first use
+        float v[9][V];
+        float edge[9];
 #pragma unroll
-            for (int c = 0; c < V; ++c) {
+        for (int k = 0; k < 9; ++k) {
+            const float *colp = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) own[c].f[k] = g[c][k];
-                own[c].rho = rho[c]; own[c].ux = ux[c]; own[c].uy = uy[c];
+            for (int c = 0; c < V; ++c) v[k][c] = 0.f;
+            edge[k] = 0.f;
+            if (lane_on) ldf<V>(colp + j0, v[k]);
+            if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = LBM_LD(colp + j0 - 1);
+            if (kEy[k] == -1 && lane == 31 && j0 + V < ny) edge[k] = LBM_LD(colp + j0 + V);
+        }
+        const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
+        float dx = 0.f;
+        float dy[V];
+        unsigned char code[V];
+#pragma unroll
+        for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; }
+        if (live) {
+            dx = __ldg(a.damp_x + il);
+            ldv<V>(a.damp_y + j0, dy);
+            ldcode<V>(a.code + (long long)il * pitch + j0, code);
+        }
+        float fin[V][9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (kEy[k] == 0) {
+#pragma unroll
+                for (int c = 0; c < V; ++c) fin[c][k] = v[k][c];
+            } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
+                float below = __shfl_up_sync(0xffffffffu, v[k][V - 1], 1);
+                if (lane == 0) below = edge[k];
+                fin[0][k] = below;
+#pragma unroll
+                for (int c = 1; c < V; ++c) fin[c][k] = v[k][c - 1];
+            } else {                   // needs j+1: first element of the lane above
+                float above = __shfl_down_sync(0xffffffffu, v[k][0], 1);
+                if (lane == 31) above = edge[k];
+#pragma unroll
+                for (int c = 0; c < V - 1; ++c) fin[c][k] = v[k][c + 1];
+                fin[V - 1][k] = above;
             }
         }
-
-        // ---- obstacle refill of interior cells (ref:452-455) and vector write-out -------------
-        // A vector made only of ring / padding cells is not written (their owners write the ring cells);
-        // otherwise non-interior slots are written as 0 and the ring slots are overwritten below by
-        // the owner -- this same thread whenever the vector holds both the ring cell and its owner.
-        bool any_interior = false;
-#pragma unroll
-        for (int c = 0; c < V; ++c) any_interior |= (j0 + c >= 1) && (j0 + c <= ny - 2);
-        if (any_interior) {
+        if (live) {
+            // collide (ref:266-420); rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
+            float g[V][9], rho[V], ux[V], uy[V];
+            bool interior[V], all_interior = true, any_interior = false;
 #pragma unroll
             for (int c = 0; c < V; ++c) {
                 const int j = j0 + c;
-                const bool interior = (j >= 1) && (j <= ny - 2);
-                if (interior && (code[c] & 1)) {
+                interior[c] = (j >= 1) && (j <= ny - 2);
+                all_interior &= interior[c];
+                any_interior |= interior[c];
+                const float damp = fmaxf(dx, dy[c]);
+#ifdef LBM_NOMATH   // experiment: pure streaming bound of this access pattern
+#pragma unroll
+                for (int k = 0; k < 9; ++k) g[c][k] = fin[c][k] + damp;
+#else
+                if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
+                else collide_fast(a.phys, fin[c], damp, g[c]);
+#endif
+                rho[c] = ux[c] = uy[c] = 0.0f;
+                if (EMIT || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+                if (code[c] & 1) {  // obstacle refill, ref:452-455
                     ux[c] = 0.0f; uy[c] = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
                 }
-                if (!interior) {
-                    rho[c] = 0.0f; ux[c] = 0.0f; uy[c] = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) g[c][k] = 0.0f;
-                }
             }
             const long long o = (long long)il * pitch + j0;
+            if (all_interior) {            // the common case: one wide store per plane
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                float t[V];
+                for (int k = 0; k < 9; ++k) {
+                    float t[V];
 #pragma unroll
-                for (int c = 0; c < V; ++c) t[c] = g[c][k];
-                stv<V>(a.dst + k * plane + o, t);
-            }
-            if (EMIT) {
-                stv<V>(a.rho + o, rho);
-                stv<V>(a.ux + o, ux);
-                stv<V>(a.uy + o, uy);
+                    for (int c = 0; c < V; ++c) t[c] = g[c][k];
+                    stv<V>(a.dst + k * plane + o, t);
+                }
+                if (EMIT) {
+                    stv<V>(a.rho + o, rho);
+                    stv<V>(a.ux + o, ux);
+                    stv<V>(a.uy + o, uy);
+                }
+            } else if (any_interior) {     // the vector shares a ring cell (ring warps write it) or padding: cell by cell
 #pragma unroll
                 for (int c = 0; c < V; ++c) {
+                    if (!interior[c]) continue;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) a.dst[k * plane + o + c] = g[c][k];
+                    if (EMIT) { a.rho[o + c] = rho[c]; a.ux[o + c] = ux[c]; a.uy[o + c] = uy[c]; }
+                }
+            }
+            if (EMIT) {
+#pragma unroll
+                for (int c = 0; c < V; ++c) {
+                    if (!interior[c]) continue;
                     const float m2 = vmag2_strict(ux[c], uy[c]);
                     vnan |= (m2 != m2);
                     vmax = fmaxf(vmax, m2);
                 }
-            }
-        }
-
-        // ---- boundary ring (ref:438-450): scalar stores, after this thread's vector stores -----
-        if (touches_ring) {
-            const int fc = *a.ctr_in + 1;
-            const float ramp = __ldg(a.ramp_tab + min(fc, a.warmup));
-            TileSink sink;
-            sink.sm_f = nullptr;
-            sink.sm_mac = nullptr;
-            sink.il0 = sink.j0 = sink.bx = sink.by = sink.row_hi = sink.col_lo = sink.col_hi = 0;
-#pragma unroll
-            for (int c = 0; c < V; ++c) {
-                const int j = j0 + c;
-                if (j < 1 || j > ny - 2) continue;
-                if (!(j == 1 || j == ny - 2 || edge_col)) continue;
-                ring_from_owner(a.ring, &sink, EMIT, il, j, &own[c], ramp, &vmax, &vnan);
             }
         }
     }

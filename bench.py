@@ -103,6 +103,8 @@ class ClockSampler:
 def build_workload(name, n_gpus):
     from benchmarks import workloads as W
 
+    if name == "random":  # BASELINE configs[3]: fixed 32768x8192 grid -> strong scaling over the slabs
+        return W.random_obstacles()
     if name == "urban" and n_gpus > 1:
         return W.urban(nx=8192 * n_gpus, ny=2048, seed=1, n_rects=100 * n_gpus, max_attempts=400 * n_gpus)
     return W.WORKLOADS[name]()
@@ -188,6 +190,13 @@ def run_ours(args):
     pkg = importlib.import_module("01-lbm-2d_b200")
 
     cfg, mask = build_workload(args.workload, world)
+    if args.grid:
+        from benchmarks import workloads as W
+
+        gx, gy = (int(v) for v in args.grid.lower().split("x"))
+        cfg, mask = W.urban(nx=gx, ny=gy, seed=1, x_lo=gx // 32, x_hi_margin=gx // 8, n_rects=max(4, gx * gy // 170000))
+    if os.environ.get("BENCH_BC"):  # experiments: boundary types, e.g. BENCH_BC=0313
+        cfg["boundary_condition"]["type"] = [int(c) for c in os.environ["BENCH_BC"]]
     nx, ny = cfg["simulation"]["nx"], cfg["simulation"]["ny"]
     if world > 1:
         from importlib import import_module
@@ -325,7 +334,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank"])
+    ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank", "random"])
+    ap.add_argument("--grid", default=None, help="NXxNY: urban-style obstacles on a custom grid (experiments)")
     ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e / cpu_baseline legs")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma", "register2", "register1", "async"])
