@@ -8,17 +8,17 @@
 
 namespace lbm {
 
-// Tuning knobs (measured on B200, 8192x2048: profiles/r01_tuning_sweep.md).  Small CTAs win: the
-// warps of a CTA move through load / math / store in lock-step, so many small CTAs per SM keep the
+// Tuning knobs (measured on B200, 8192x2048: profiles/r01_tuning_sweep.md).  Small CTAs (64-128 threads) win:
+// the warps of a CTA move through load / math / store in lock-step, so many small CTAs per SM keep the
 // memory pipeline evenly fed.
 #ifndef LBM_WPB
-#define LBM_WPB 2
+#define LBM_WPB 4
 #endif
 #ifndef LBM_MINB2
-#define LBM_MINB2 16
+#define LBM_MINB2 8
 #endif
 #ifndef LBM_MINB1
-#define LBM_MINB1 24
+#define LBM_MINB1 12
 #endif
 #ifndef LBM_STCS
 #define LBM_STCS 0
