@@ -78,7 +78,6 @@ struct LbmSolver {
     LbmParams p{};
     nccl::Comm comm = nullptr;
     int rank = 0, nranks = 1;
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // 32 plain steps starting at parity 0 / 1 (launch-bound grids)
     cudaStream_t stream_e = nullptr;   // edge columns + halo exchange, overlapped with the interior
     cudaEvent_t ev_m = nullptr, ev_e = nullptr, ev_e_prev = nullptr, ev_x = nullptr;
     bool ev_e_prev_valid = false;
@@ -100,6 +99,7 @@ struct LbmSolver {
     bool use_tma = false;
     int vwidth = 4;  // cells per thread of the register variant
     bool use_async = false;
+    bool use_pdl = true;
     int async_grid = 0;
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
@@ -126,8 +126,6 @@ struct LbmSolver {
     ~LbmSolver() {
         cudaSetDevice(device);
         if (comm) nccl::api().CommDestroy(comm);
-        for (cudaGraphExec_t g : graph)
-            if (g) cudaGraphExecDestroy(g);
         for (cudaEvent_t ev : {ev_m, ev_e, ev_e_prev, ev_x})
             if (ev) cudaEventDestroy(ev);
         if (stream_e) cudaStreamDestroy(stream_e);
@@ -352,6 +350,29 @@ int exchange_halos(LbmSolver *s, float *buf, cudaStream_t st) {
     return LBM_OK;
 }
 
+typedef void (*StepFn)(const lbm::StepArgs);
+StepFn step_fn(bool strict, bool emit, int v) {
+#define LBM_PICK(S, E) (v == 4 ? (StepFn)lbm::step_kernel<S, E, 4> : v == 2 ? (StepFn)lbm::step_kernel<S, E, 2> : (StepFn)lbm::step_kernel<S, E, 1>)
+    return strict ? (emit ? LBM_PICK(true, true) : LBM_PICK(true, false)) : (emit ? LBM_PICK(false, true) : LBM_PICK(false, false));
+#undef LBM_PICK
+}
+
+// Launch one step of the register variant.  `pdl`: programmatic dependent launch -- the grid may start being
+// scheduled before the previous kernel in the stream has drained (it synchronises on it itself, see the kernel).
+cudaError_t launch_step(StepFn fn, dim3 grid, cudaStream_t st, const lbm::StepArgs &a, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(lbm::kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fn, a);
+}
+
 int check_handle(LbmHandle h, bool need_init) {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
     if (need_init && !h->inited) return fail(LBM_ERR_STATE, "lbm_init() has not been called");
@@ -538,6 +559,7 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         (void)tiles;
         s->use_tma = p.kernel == LBM_KERNEL_TMA;
         s->use_async = p.kernel == LBM_KERNEL_ASYNC;
+        s->use_pdl = !std::getenv("LBM2D_NO_PDL");
         if (s->use_async) {
             const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
             int per_sm = 0;
@@ -634,33 +656,7 @@ int lbm_run(LbmHandle h, int steps) {
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
     }
-    // Launch-bound grids (a step of the L2-resident BASELINE configs is a few microseconds of GPU work): replay
-    // a captured CUDA graph of kGraphSteps plain steps; the tail and the EMIT step are launched directly.
-    constexpr int kGraphSteps = 32;
-    int done_by_graph = 0;
-    if (!h->comm && !h->use_tma && !h->use_async && h->plane <= (1LL << 22) && steps - 1 >= kGraphSteps && !std::getenv("LBM2D_NO_GRAPH")) {
-        const int par0 = (int)(h->steps_done & 1);
-        if (!h->graph[par0]) {
-            cudaGraph_t g = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            for (int i = 0; i < kGraphSteps; ++i) {
-                const lbm::StepArgs a = make_args(h, (par0 + i) & 1);
-                if (h->vwidth == 4) { if (strict) lbm::step_kernel<true, false, 4><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 4><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
-                else if (h->vwidth == 2) { if (strict) lbm::step_kernel<true, false, 2><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 2><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
-                else { if (strict) lbm::step_kernel<true, false, 1><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); else lbm::step_kernel<false, false, 1><<<blocks_all, lbm::kThreads, 0, h->stream>>>(a); }
-            }
-            CUDA_TRY(cudaStreamEndCapture(h->stream, &g));
-            CUDA_TRY(cudaGraphInstantiate(&h->graph[par0], g, 0));
-            CUDA_TRY(cudaGraphDestroy(g));
-        }
-        while (steps - 1 - done_by_graph >= kGraphSteps) {
-            CUDA_TRY(cudaGraphLaunch(h->graph[par0], h->stream));
-            done_by_graph += kGraphSteps;
-            h->steps_done += kGraphSteps;   // even: the parity, and so the graph, stays the same
-            h->launches += kGraphSteps;
-        }
-    }
-    for (int it = done_by_graph; it < steps; ++it) {
+    for (int it = 0; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
         if (h->use_tma) {
@@ -722,17 +718,9 @@ int lbm_run(LbmHandle h, int steps) {
             if (strict) { if (emit) lbm::step_async_kernel<true, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<true, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
             else { if (emit) lbm::step_async_kernel<false, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<false, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
         } else {
-#define LBM_LAUNCH_REG(S, E, V) lbm::step_kernel<S, E, V><<<blocks, lbm::kThreads, 0, st>>>(a)
-#define LBM_LAUNCH_V(V)                                                     \
-    do {                                                                    \
-        if (strict) { if (emit) LBM_LAUNCH_REG(true, true, V); else LBM_LAUNCH_REG(true, false, V); } \
-        else { if (emit) LBM_LAUNCH_REG(false, true, V); else LBM_LAUNCH_REG(false, false, V); }      \
-    } while (0)
-        if (h->vwidth == 4) LBM_LAUNCH_V(4);
-        else if (h->vwidth == 2) LBM_LAUNCH_V(2);
-        else LBM_LAUNCH_V(1);
-#undef LBM_LAUNCH_V
-#undef LBM_LAUNCH_REG
+            // PDL between consecutive plain steps of a batch (not across the max|u| memset of an EMIT step)
+            const bool pdl = h->use_pdl && !overlap && !emit && it > 0;
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth), blocks, st, a, pdl));
         }
         h->steps_done++;
         h->launches++;

@@ -191,6 +191,10 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 // the columns): one ring cell per lane, see above.
 template <bool STRICT, bool EMIT, int V>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
+    // Programmatic dependent launch: the next step's grid may be scheduled while this one drains, and waits
+    // here until this grid's writes are complete and visible (a no-op for ordinary launches).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     // grid: x = blocks of segments down a column, y (+ z beyond 65535) = interior column, then ring rows
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
