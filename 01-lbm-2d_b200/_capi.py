@@ -55,6 +55,7 @@ EXPORTS = {
     "lbm_get_moments": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_f": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "lbm_export_configure": (C.c_int, [C.c_void_p, C.POINTER(LbmExportConfig)]),
+    "lbm_export_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lbm_export_frame": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_export_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -41,7 +41,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 namespace nccl {
 typedef struct { char internal[128]; } UniqueId;
 typedef void *Comm;
-enum { kFloat32 = 7 };
+enum { kInt32 = 2, kFloat32 = 7 };
 struct Api {
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
@@ -111,6 +111,9 @@ struct LbmSolver {
     int *exp_xoff = nullptr, *exp_yoff = nullptr;
     float *exp_tmp = nullptr, *exp_frame = nullptr;
     double *exp_sum = nullptr, *exp_velsq = nullptr, *exp_vor = nullptr, *exp_minmax = nullptr;
+    float *exp_halo = nullptr;      // [4][3*th]: send-west, send-east, recv-from-west (left), recv-from-east (right)
+    int *exp_ecount = nullptr;      // [2] device scratch for the one-off extension-width handshake
+    int exp_send_cols = 0, exp_recv_cols = 0;   // ROI columns sent to the west / received from the east neighbour
     int64_t exp_count = 0;
     lbm::Link *links = nullptr;
     int n_links = 0;
@@ -133,7 +136,7 @@ struct LbmSolver {
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
-                          (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax})
+                          (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount})
             if (ptr) cudaFree(ptr);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -855,40 +858,81 @@ static double area_tab(int ssize, int dsize, std::vector<lbm::AreaEntry> &tab, s
 int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     if (int rc = check_handle(h, false)) return rc;
     if (!cfg) return fail(LBM_ERR_INVALID, "cfg is null");
-    if (h->p.nx != h->p.nx_global) return fail(LBM_ERR_INVALID, "export reduction is implemented for single-GPU handles");
-    const int cw = cfg->x1 - cfg->x0, ch = cfg->y1 - cfg->y0;
-    if (cfg->x0 < 0 || cfg->y0 < 0 || cfg->x1 > h->p.nx || cfg->y1 > h->ny || cw <= 0 || ch <= 0)
+    const bool slabs = h->p.nx != h->p.nx_global;
+    if (slabs && !h->comm) return fail(LBM_ERR_STATE, "slab handles need lbm_comm_connect() before lbm_export_configure()");
+    const int X0 = cfg->x0, X1 = cfg->x1, cw_g = X1 - X0, ch = cfg->y1 - cfg->y0;
+    if (X0 < 0 || cfg->y0 < 0 || X1 > h->p.nx_global || cfg->y1 > h->ny || cw_g <= 0 || ch <= 0)
         return fail(LBM_ERR_INVALID, "export ROI outside the grid or empty");
-    if (cfg->target_w < 1 || cfg->target_h < 1 || cfg->target_w > cw || cfg->target_h > ch)
+    if (cfg->target_w < 1 || cfg->target_h < 1 || cfg->target_w > cw_g || cfg->target_h > ch)
         return fail(LBM_ERR_INVALID, "INTER_AREA export supports shrinking only (1 <= target <= crop)");
-    for (void *ptr : {(void *)h->exp_xtab, (void *)h->exp_ytab, (void *)h->exp_xoff, (void *)h->exp_yoff, (void *)h->exp_tmp,
-                      (void *)h->exp_frame, (void *)h->exp_sum, (void *)h->exp_velsq, (void *)h->exp_vor, (void *)h->exp_minmax})
-        if (ptr) cudaFree(ptr);
-    h->exp_xtab = h->exp_ytab = nullptr;
-    h->exp_xoff = h->exp_yoff = nullptr;
-    h->exp_tmp = h->exp_frame = nullptr;
-    h->exp_sum = h->exp_velsq = h->exp_vor = h->exp_minmax = nullptr;
+    for (void **ptr : {(void **)&h->exp_xtab, (void **)&h->exp_ytab, (void **)&h->exp_xoff, (void **)&h->exp_yoff, (void **)&h->exp_tmp,
+                       (void **)&h->exp_frame, (void **)&h->exp_sum, (void **)&h->exp_velsq, (void **)&h->exp_vor,
+                       (void **)&h->exp_minmax, (void **)&h->exp_halo, (void **)&h->exp_ecount}) {
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr;
+    }
     h->exp_ready = false;
 
-    lbm::ExportGeom &g = h->exp_geom;
-    g.x0 = cfg->x0; g.y0 = cfg->y0; g.cw = cw; g.ch = ch; g.tw = cfg->target_w; g.th = cfg->target_h;
     std::vector<lbm::AreaEntry> xt, yt;
     std::vector<int> xo, yo;
-    const double sx = area_tab(cw, g.tw, xt, xo), sy = area_tab(ch, g.th, yt, yo);
+    const double sx = area_tab(cw_g, cfg->target_w, xt, xo), sy = area_tab(ch, cfg->target_h, yt, yo);
+    lbm::ExportGeom &g = h->exp_geom;
+    g.tw_g = cfg->target_w;
+    g.th = cfg->target_h;
+    g.ch = ch;
+    g.y0 = cfg->y0;
     g.ix = (int)std::lrint(sx);
     g.iy = (int)std::lrint(sy);
     g.fast = std::fabs(sx - g.ix) < 2.220446049250313e-16 && std::fabs(sy - g.iy) < 2.220446049250313e-16;
-    const size_t npx = (size_t)g.tw * g.th;
+    // this rank's share: the ROI columns it owns, and the output columns whose first source column is one of them
+    const int gx0 = h->p.slab_x0, gx1 = h->p.slab_x0 + h->p.nx;
+    const int rx0 = std::min(std::max(gx0, X0), X1), rx1 = std::max(std::min(gx1, X1), rx0);
+    g.own_cols = rx1 - rx0;
+    g.x0 = rx0 - h->x_off;
+    g.src_shift = rx0 - X0;
+    int dlo = 0, dhi = 0;
+    for (int dx = 0; dx < g.tw_g; ++dx) {
+        const int first = X0 + xt[xo[dx]].si;
+        if (first < rx0) ++dlo;
+        if (first < rx1) ++dhi;
+    }
+    if (g.own_cols == 0) dhi = dlo;
+    g.dlo = dlo;
+    g.dhi = dhi;
+    int e_recv = 0;
+    if (dhi > dlo) e_recv = std::max(0, X0 + xt[xo[dhi] - 1].si - (rx1 - 1));
+    int e_send = 0;
+    CUDA_TRY(cudaMalloc(&h->exp_ecount, 2 * sizeof(int)));
+    if (slabs) {  // tell the east neighbour how many of its first ROI columns this rank needs
+        nccl::Api &n = nccl::api();
+        CUDA_TRY(cudaMemcpyAsync(h->exp_ecount, &e_recv, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->exp_ecount + 1, 0, sizeof(int), h->stream));
+        NCCL_TRY(n.GroupStart());
+        if (!h->east_ring) NCCL_TRY(n.Send(h->exp_ecount, 1, nccl::kInt32, h->rank + 1, h->comm, h->stream));
+        if (!h->west_ring) NCCL_TRY(n.Recv(h->exp_ecount + 1, 1, nccl::kInt32, h->rank - 1, h->comm, h->stream));
+        NCCL_TRY(n.GroupEnd());
+        CUDA_TRY(cudaMemcpyAsync(&e_send, h->exp_ecount + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (e_send > g.own_cols) return fail(LBM_ERR_INVALID, "slab too narrow for the export reduction (neighbour needs more ROI columns than this rank owns)");
+    } else if (e_recv != 0) {
+        return fail(LBM_ERR_INVALID, "internal: single-GPU export needs no extension");
+    }
+    h->exp_send_cols = e_send;
+    h->exp_recv_cols = e_recv;
+    g.cw = g.own_cols + e_recv;
+
+    const size_t npx = (size_t)std::max(1, dhi - dlo) * g.th;
     CUDA_TRY(cudaMalloc(&h->exp_xtab, xt.size() * sizeof(lbm::AreaEntry)));
     CUDA_TRY(cudaMalloc(&h->exp_ytab, yt.size() * sizeof(lbm::AreaEntry)));
     CUDA_TRY(cudaMalloc(&h->exp_xoff, xo.size() * sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->exp_yoff, yo.size() * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&h->exp_tmp, (size_t)9 * cw * ch * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->exp_tmp, (size_t)9 * std::max(1, g.cw) * ch * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->exp_frame, 9 * npx * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->exp_sum, 9 * npx * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->exp_velsq, npx * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->exp_vor, npx * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->exp_minmax, 18 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->exp_halo, (size_t)4 * 3 * g.th * sizeof(float)));
     CUDA_TRY(cudaMemcpy(h->exp_xtab, xt.data(), xt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->exp_ytab, yt.data(), yt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->exp_xoff, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -896,6 +940,7 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     CUDA_TRY(cudaMemset(h->exp_sum, 0, 9 * npx * sizeof(double)));
     CUDA_TRY(cudaMemset(h->exp_velsq, 0, npx * sizeof(double)));
     CUDA_TRY(cudaMemset(h->exp_vor, 0, npx * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->exp_halo, 0, (size_t)4 * 3 * g.th * sizeof(float)));
     double mm[18];
     for (int c = 0; c < 9; ++c) { mm[c] = INFINITY; mm[9 + c] = -INFINITY; }
     CUDA_TRY(cudaMemcpy(h->exp_minmax, mm, sizeof(mm), cudaMemcpyHostToDevice));
@@ -904,22 +949,70 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     return LBM_OK;
 }
 
+int lbm_export_layout(LbmHandle h, int32_t *dlo, int32_t *dhi, int32_t *target_h) {
+    if (!h || !h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
+    if (dlo) *dlo = h->exp_geom.dlo;
+    if (dhi) *dhi = h->exp_geom.dhi;
+    if (target_h) *target_h = h->exp_geom.th;
+    return LBM_OK;
+}
+
 int lbm_export_frame(LbmHandle h, float *out_chw) {
     if (int rc = check_handle(h, true)) return rc;
     if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
     const lbm::ExportGeom g = h->exp_geom;
     const lbm::ExportArgs a = make_export_args(h);
-    const size_t npx = (size_t)g.tw * g.th;
-    lbm::roi_moments_kernel<<<dim3((g.ch + 127) / 128, g.cw), 128, 0, h->stream>>>(a, g, h->exp_tmp);
-    const dim3 rgrid((g.th + 63) / 64, g.tw, 9);
-    if (g.fast) lbm::area_fast_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_frame);
-    else lbm::area_resize_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_xtab, h->exp_xoff, h->exp_ytab, h->exp_yoff, h->exp_frame);
-    lbm::export_stats_kernel<<<dim3((g.tw + 127) / 128, g.th), 128, 0, h->stream>>>(h->exp_frame, g.tw, g.th, h->exp_sum, h->exp_velsq, h->exp_vor);
-    lbm::export_minmax_kernel<<<9, 256, 0, h->stream>>>(h->exp_frame, (long long)npx, h->exp_minmax, h->exp_minmax + 9);
+    const int twl = g.dhi - g.dlo;
+    const size_t npx = (size_t)twl * g.th;
+    const bool slabs = h->comm && h->nranks > 1;
+    nccl::Api &n = nccl::api();
+    if (g.own_cols > 0) {
+        lbm::roi_moments_kernel<<<dim3((g.ch + 127) / 128, g.own_cols), 128, 0, h->stream>>>(a, g, h->exp_tmp);
+        h->launches++;
+    }
+    if (slabs && (h->exp_send_cols > 0 || h->exp_recv_cols > 0)) {
+        // the last output columns of a rank reach into the first ROI columns of its east neighbour
+        const size_t pl = (size_t)g.cw * g.ch;
+        NCCL_TRY(n.GroupStart());
+        for (int c = 0; c < 9; ++c) {
+            if (h->exp_send_cols > 0) NCCL_TRY(n.Send(h->exp_tmp + c * pl, (size_t)h->exp_send_cols * g.ch, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+            if (h->exp_recv_cols > 0) NCCL_TRY(n.Recv(h->exp_tmp + c * pl + (size_t)g.own_cols * g.ch, (size_t)h->exp_recv_cols * g.ch, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+        }
+        NCCL_TRY(n.GroupEnd());
+    }
+    if (twl > 0) {
+        const dim3 rgrid((g.th + 63) / 64, twl, 9);
+        if (g.fast) lbm::area_fast_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_frame);
+        else lbm::area_resize_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_xtab, h->exp_xoff, h->exp_ytab, h->exp_yoff, h->exp_frame);
+        h->launches++;
+    }
+    // x-gradient halos: rho, jx, jy of the neighbours' adjacent output columns
+    float *send_w = h->exp_halo, *send_e = h->exp_halo + 3 * g.th, *left = h->exp_halo + 6 * g.th, *right = h->exp_halo + 9 * g.th;
+    const bool nb_w = slabs && twl > 0 && g.dlo > 0, nb_e = slabs && twl > 0 && g.dhi < g.tw_g;
+    if (slabs) {
+        // every rank takes part; a rank without output columns forwards nothing (its neighbours' columns are then
+        // not adjacent to it, which only happens at the ends of the ROI where the global edge rule applies)
+        if (nb_w) lbm::export_pack_column_kernel<<<(g.th + 127) / 128, 128, 0, h->stream>>>(h->exp_frame, twl, g.th, 0, send_w);
+        if (nb_e) lbm::export_pack_column_kernel<<<(g.th + 127) / 128, 128, 0, h->stream>>>(h->exp_frame, twl, g.th, twl - 1, send_e);
+        NCCL_TRY(n.GroupStart());
+        if (!h->west_ring) {
+            NCCL_TRY(n.Send(send_w, 3 * g.th, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+            NCCL_TRY(n.Recv(left, 3 * g.th, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+        }
+        if (!h->east_ring) {
+            NCCL_TRY(n.Send(send_e, 3 * g.th, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+            NCCL_TRY(n.Recv(right, 3 * g.th, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+        }
+        NCCL_TRY(n.GroupEnd());
+    }
+    if (twl > 0) {
+        lbm::export_stats_kernel<<<dim3((twl + 127) / 128, g.th), 128, 0, h->stream>>>(h->exp_frame, twl, g.th, g.dlo, g.tw_g, left, right, h->exp_sum, h->exp_velsq, h->exp_vor);
+        lbm::export_minmax_kernel<<<9, 256, 0, h->stream>>>(h->exp_frame, (long long)npx, h->exp_minmax, h->exp_minmax + 9);
+        h->launches += 2;
+    }
     CUDA_TRY(cudaGetLastError());
-    h->launches += 4;
     h->exp_count++;
-    if (out_chw) CUDA_TRY(cudaMemcpyAsync(out_chw, h->exp_frame, 9 * npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (out_chw && twl > 0) CUDA_TRY(cudaMemcpyAsync(out_chw, h->exp_frame, 9 * npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
@@ -928,10 +1021,12 @@ int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw
                      double *max9, int64_t *count) {
     if (int rc = check_handle(h, false)) return rc;
     if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
-    const size_t npx = (size_t)h->exp_geom.tw * h->exp_geom.th;
-    if (running_sum_chw) CUDA_TRY(cudaMemcpyAsync(running_sum_chw, h->exp_sum, 9 * npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (vel_sq_sum_hw) CUDA_TRY(cudaMemcpyAsync(vel_sq_sum_hw, h->exp_velsq, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (abs_vor_sum_hw) CUDA_TRY(cudaMemcpyAsync(abs_vor_sum_hw, h->exp_vor, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t npx = (size_t)(h->exp_geom.dhi - h->exp_geom.dlo) * h->exp_geom.th;
+    if (npx > 0) {
+        if (running_sum_chw) CUDA_TRY(cudaMemcpyAsync(running_sum_chw, h->exp_sum, 9 * npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (vel_sq_sum_hw) CUDA_TRY(cudaMemcpyAsync(vel_sq_sum_hw, h->exp_velsq, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (abs_vor_sum_hw) CUDA_TRY(cudaMemcpyAsync(abs_vor_sum_hw, h->exp_vor, npx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     if (min9) CUDA_TRY(cudaMemcpyAsync(min9, h->exp_minmax, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (max9) CUDA_TRY(cudaMemcpyAsync(max9, h->exp_minmax + 9, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));

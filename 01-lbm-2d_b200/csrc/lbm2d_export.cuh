@@ -16,9 +16,17 @@ struct AreaEntry {
     float alpha;  // weight (float, as OpenCV's DecimateAlpha)
 };
 
+// Geometry of one rank's share of the export.  Single GPU: own_cols = cw = crop width, dlo = 0, dhi = tw_g.
+// x-slabs: a rank computes the moments of its own ROI columns, receives the few columns its last output
+// pixels reach into from the east neighbour, and produces the output columns [dlo, dhi) whose FIRST source
+// column it owns -- so the assembled frame is the global cv2 result, independent of the decomposition.
 struct ExportGeom {
-    int x0, y0, cw, ch;  // ROI origin (local column, row) and size
-    int tw, th;          // target size
+    int x0, y0;          // first own ROI column (local index), first ROI row
+    int own_cols;        // ROI columns computed locally
+    int cw, ch;          // columns held in tmp (own_cols + received extension), rows
+    int src_shift;       // global ROI-relative source column  -  src_shift  =  tmp column
+    int tw_g, th;        // GLOBAL target width, target height
+    int dlo, dhi;        // output columns of this rank
     int fast;            // both scales integer: resizeAreaFast_ path
     int ix, iy;          // integer scales (fast path)
 };
@@ -26,7 +34,7 @@ struct ExportGeom {
 // 9 moments of the reference's f_new over the ROI -> tmp[c][x][y] (y fastest)
 __global__ void roi_moments_kernel(const ExportArgs a, ExportGeom g, float *__restrict__ tmp) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    const int x = blockIdx.y;
+    const int x = blockIdx.y;   // < own_cols
     if (y >= g.ch) return;
     float f[9], m[9];
     load_f_new(a, g.x0 + x, g.y0 + y, f);
@@ -42,7 +50,7 @@ __global__ void area_resize_kernel(const float *__restrict__ tmp, ExportGeom g, 
                                    const int *__restrict__ xoff, const AreaEntry *__restrict__ ytab,
                                    const int *__restrict__ yoff, float *__restrict__ out) {
     const int dy = blockIdx.x * blockDim.x + threadIdx.x;  // lanes along y: neighbouring source rows
-    const int dx = blockIdx.y, c = blockIdx.z;
+    const int dxl = blockIdx.y, dx = g.dlo + dxl, c = blockIdx.z;
     if (dy >= g.th) return;
     const float *S = tmp + (long long)c * g.cw * g.ch;
     float total = 0.0f;
@@ -50,20 +58,21 @@ __global__ void area_resize_kernel(const float *__restrict__ tmp, ExportGeom g, 
     for (int j = yoff[dy]; j < yoff[dy + 1]; ++j) {
         const int sy = ytab[j].si;
         float buf = 0.0f;
-        for (int k = k0; k < k1; ++k) buf = __fadd_rn(buf, __fmul_rn(S[(long long)xtab[k].si * g.ch + sy], xtab[k].alpha));
+        for (int k = k0; k < k1; ++k)
+            buf = __fadd_rn(buf, __fmul_rn(S[(long long)(xtab[k].si - g.src_shift) * g.ch + sy], xtab[k].alpha));
         total = __fadd_rn(total, __fmul_rn(ytab[j].alpha, buf));
     }
-    out[((long long)c * g.th + dy) * g.tw + dx] = total;
+    out[((long long)c * g.th + dy) * (g.dhi - g.dlo) + dxl] = total;
 }
 
 // resizeAreaFast_: integer scales.  2x2: ((a+b)+(c+d))*0.25 (the SIMD kernel); otherwise the scalar loop
 // unrolled by four the way OpenCV writes it, times 1/area.
 __global__ void area_fast_kernel(const float *__restrict__ tmp, ExportGeom g, float *__restrict__ out) {
     const int dy = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dx = blockIdx.y, c = blockIdx.z;
+    const int dxl = blockIdx.y, dx = g.dlo + dxl, c = blockIdx.z;
     if (dy >= g.th) return;
     const float *S = tmp + (long long)c * g.cw * g.ch;
-    auto at = [&](int sy, int sx) { return S[(long long)sx * g.ch + sy]; };
+    auto at = [&](int sy, int sx) { return S[(long long)(sx - g.src_shift) * g.ch + sy]; };
     float r;
     if (g.ix == 2 && g.iy == 2) {
         const float a = at(2 * dy, 2 * dx), b = at(2 * dy, 2 * dx + 1), cc = at(2 * dy + 1, 2 * dx), d = at(2 * dy + 1, 2 * dx + 1);
@@ -78,34 +87,54 @@ __global__ void area_fast_kernel(const float *__restrict__ tmp, ExportGeom g, fl
         for (; k < area; ++k) sum = __fadd_rn(sum, val(k));
         r = __fmul_rn(sum, 1.0f / (float)area);
     }
-    out[((long long)c * g.th + dy) * g.tw + dx] = r;
+    out[((long long)c * g.th + dy) * (g.dhi - g.dlo) + dxl] = r;
+}
+
+// Channels 0 (rho), 3 (jx), 5 (jy) of one frame column -> buf[3][th] (halo for the neighbour's x-gradient).
+__global__ void export_pack_column_kernel(const float *__restrict__ frame, int twl, int th, int xl, float *__restrict__ buf) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= th) return;
+    const long long n = (long long)twl * th, q = (long long)y * twl + xl;
+    buf[y] = frame[q];
+    buf[th + y] = frame[3 * n + q];
+    buf[2 * th + y] = frame[5 * n + q];
 }
 
 // writer:176-210: running sum of the frame (float64), sum of u^2+v^2, sum of |vorticity| on the
-// down-sampled grid (np.gradient: central differences inside, one-sided at the edges, float32).
-__global__ void export_stats_kernel(const float *__restrict__ frame, int tw, int th, double *__restrict__ running_sum,
-                                    double *__restrict__ vel_sq_sum, double *__restrict__ abs_vor_sum) {
+// down-sampled grid (np.gradient: central differences inside, one-sided at the GLOBAL edges, float32).
+// `left` / `right`: rho, jx, jy of the output columns dlo-1 / dhi held by the neighbouring ranks (or null).
+__global__ void export_stats_kernel(const float *__restrict__ frame, int twl, int th, int dlo, int tw_g,
+                                    const float *__restrict__ left, const float *__restrict__ right,
+                                    double *__restrict__ running_sum, double *__restrict__ vel_sq_sum,
+                                    double *__restrict__ abs_vor_sum) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= tw) return;
-    const long long n = (long long)tw * th, o = (long long)y * tw + x;
+    if (x >= twl) return;
+    const long long n = (long long)twl * th, o = (long long)y * twl + x;
 #pragma unroll
     for (int c = 0; c < 9; ++c) running_sum[c * n + o] += (double)frame[c * n + o];
-    auto uv = [&](int yy, int xx, float &u, float &v) {
-        const long long q = (long long)yy * tw + xx;
-        const float rs = fmaxf(frame[q], 1e-6f);
-        u = __fdiv_rn(frame[3 * n + q], rs);
-        v = __fdiv_rn(frame[5 * n + q], rs);
+    auto uv = [&](int yy, int xx, float &u, float &v) {   // xx = -1 / twl read the neighbours' halo columns
+        float rho, jx, jy;
+        if (xx < 0) { rho = left[yy]; jx = left[th + yy]; jy = left[2 * th + yy]; }
+        else if (xx >= twl) { rho = right[yy]; jx = right[th + yy]; jy = right[2 * th + yy]; }
+        else {
+            const long long q = (long long)yy * twl + xx;
+            rho = frame[q]; jx = frame[3 * n + q]; jy = frame[5 * n + q];
+        }
+        const float rs = fmaxf(rho, 1e-6f);
+        u = __fdiv_rn(jx, rs);
+        v = __fdiv_rn(jy, rs);
     };
     float u, v;
     uv(y, x, u, v);
     vel_sq_sum[o] += (double)__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v));
     // dv/dx along W (axis 1), du/dy along H (axis 0)
     float ua, va, ub, vb, dvdx = 0.0f, dudy = 0.0f;
-    if (tw > 1) {
-        const int xa = x == 0 ? 0 : x - 1, xb = x == tw - 1 ? tw - 1 : x + 1;
-        uv(y, xa, ua, va);
-        uv(y, xb, ub, vb);
-        dvdx = (x == 0 || x == tw - 1) ? __fsub_rn(vb, va) : __fdiv_rn(__fsub_rn(vb, va), 2.0f);
+    const int xg = dlo + x;
+    if (tw_g > 1) {
+        const bool first = xg == 0, last = xg == tw_g - 1;
+        uv(y, first ? x : x - 1, ua, va);
+        uv(y, last ? x : x + 1, ub, vb);
+        dvdx = (first || last) ? __fsub_rn(vb, va) : __fdiv_rn(__fsub_rn(vb, va), 2.0f);
     }
     if (th > 1) {
         const int ya = y == 0 ? 0 : y - 1, yb = y == th - 1 ? th - 1 : y + 1;

@@ -80,6 +80,18 @@ class DeviceLBMCaseWriter:
             return None
         self.is_closed = True
         st = self._solver.export_stats() if self._solver is not None else {"running_count": 0}
+        frames = np.stack(self.frames, axis=0) if self.frames else None
+        if getattr(self._solver, "world", 1) > 1:
+            # x-slabs: every rank holds a column range of the global frame; assemble on rank 0
+            sv = self._solver
+            frames = sv.gather_columns(frames if frames is not None else np.zeros((0, 9, self.target_h, 0), np.float32))
+            parts = {k: sv.gather_columns(st[k]) for k in ("running_sum", "running_vel_sq_sum", "sum_abs_vor")}
+            mins = sv.gather_columns(st["global_min"][:, None])
+            maxs = sv.gather_columns(st["global_max"][:, None])
+            if sv.rank != 0:
+                self.result, self.attrs = None, None
+                return None
+            st = dict(st, **parts, global_min=mins.min(axis=1), global_max=maxs.max(axis=1))
         out = {}
         if self.static_mask is not None:
             out["static_mask"] = self.static_mask
@@ -87,7 +99,7 @@ class DeviceLBMCaseWriter:
             n = st["running_count"]
             mean_field = (st["running_sum"] / n).astype(np.float32)              # writer:224-233
             out.update(
-                turbulence=np.stack(self.frames, axis=0) if self.frames else np.zeros((0, 9, self.target_h, self.target_w), np.float32),
+                turbulence=frames if frames is not None else np.zeros((0, 9, self.target_h, self.target_w), np.float32),
                 mean_vel_field=mean_field,
                 mean_vel_sq_field=(st["running_vel_sq_sum"] / n).astype(np.float32),
                 sum_vor=st["sum_abs_vor"].astype(np.float32),

@@ -137,6 +137,25 @@ class SlabLBM:
     def get_physical_fields(self):
         return self.solver.get_physical_fields()
 
+    # ---- on-device export reduction: ROI / target are global, every rank holds a column range of the frame ----
+    def export_configure(self, x0, x1, y0, y1, target_w, target_h):
+        self.solver.export_configure(x0, x1, y0, y1, target_w, target_h)
+        self.export_columns = self.solver.export_columns
+
+    def export_frame(self, want_frame=True):
+        return self.solver.export_frame(want_frame)
+
+    def export_stats(self):
+        return self.solver.export_stats()
+
+    def gather_columns(self, local):
+        """Concatenate per-rank arrays along their LAST axis (output columns) on rank 0 (None elsewhere)."""
+        if self.world == 1:
+            return local
+        parts = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(local, parts, dst=0)
+        return np.concatenate(parts, axis=-1) if self.rank == 0 else None
+
     def gather(self, local):
         """Concatenate per-rank owned-column arrays along x on rank 0 (None elsewhere)."""
         if self.world == 1:

@@ -158,7 +158,10 @@ class LBM2D_MRT_LES:
         """ROI crop + INTER_AREA target of the reference writer (io/lbm_writer.py:37-58); resets the statistics."""
         cfg = _capi.LbmExportConfig(int(x0), int(x1), int(y0), int(y1), int(target_w), int(target_h))
         _capi.check(self._lib.lbm_export_configure(self._h, C.byref(cfg)))
-        self._export_shape = (9, int(target_h), int(target_w))
+        dlo, dhi, th = C.c_int32(), C.c_int32(), C.c_int32()
+        _capi.check(self._lib.lbm_export_layout(self._h, C.byref(dlo), C.byref(dhi), C.byref(th)))
+        self.export_columns = (int(dlo.value), int(dhi.value))   # this rank's columns of the global frame
+        self._export_shape = (9, int(target_h), int(dhi.value - dlo.value))
 
     def export_frame(self, want_frame=True):
         """One export frame (9, H, W): moments -> crop -> INTER_AREA on the GPU, statistics accumulated there."""

@@ -251,13 +251,12 @@ def run_ours(args):
     ops = importlib.import_module("01-lbm-2d_b200.simulation_ops")
     e2e = {}
     for label in (("device_writer", "full_frame") if not args.quick else ("device_writer",)):
-        if world > 1 and label == "device_writer":
-            continue  # the export reduction is single-GPU in round 1; slabs hand out their full frames
         writer = None
         if label == "device_writer":
             dwm = importlib.import_module("01-lbm-2d_b200.device_writer")
             writer = dwm.DeviceLBMCaseWriter(os.path.join(ROOT, "gpurun_out", "bench_case.h5"), cfg, nx, ny, solver=solver)
-            frame_bytes = 9 * writer.target_w * writer.target_h * 4
+            lo, hi = solver.export_columns if hasattr(solver, "export_columns") else (0, writer.target_w)
+            frame_bytes = 9 * writer.target_w * writer.target_h * 4   # whole job; this rank holds columns [lo, hi)
         else:
             class _FullFrame:  # what the reference's AsyncLBMCaseWriter receives
                 n = 0
@@ -266,7 +265,7 @@ def run_ours(args):
                     self.n += m.nbytes
 
             writer = _FullFrame()
-            frame_bytes = nx * ny * 9 * 4 // world
+            frame_bytes = nx * ny * 9 * 4   # whole job, nx*ny*9*4/world per rank
         barrier()
         t0 = time.perf_counter()
         meta = ops.run_simulation_loop(cfg, solver, None, None, None, writer, max_steps=n_batches * css, progress=False)

@@ -132,12 +132,16 @@ int lbm_get_f(LbmHandle h, int which, float *out_nxny9);
  * down-sampled per channel exactly like cv2.resize(..., INTER_AREA) (lbm_writer.py:150-163), accumulated
  * into the running sum / min / max / sum(u^2+v^2) / sum|vorticity| (lbm_writer.py:176-210) on the device;
  * `out_chw` (9, target_h, target_w) fp32 receives the frame (may be NULL).  lbm_export_stats(): the
- * accumulators for finalize() (lbm_writer.py:212-251); any pointer may be NULL.  Single-GPU handles only. */
+ * accumulators for finalize() (lbm_writer.py:212-251); any pointer may be NULL. */
 typedef struct {
     int32_t x0, x1, y0, y1;
     int32_t target_w, target_h;
 } LbmExportConfig;
 int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg);
+/* x-slabs: ROI and target are GLOBAL; every rank calls the export functions collectively and holds the output
+ * columns [dlo, dhi) of the global (9, target_h, target_w) frame (those whose first source column it owns), so
+ * the concatenation over ranks is the single-GPU / cv2 result.  lbm_export_frame() then fills (9, target_h, dhi-dlo). */
+int lbm_export_layout(LbmHandle h, int32_t *dlo, int32_t *dhi, int32_t *target_h);
 int lbm_export_frame(LbmHandle h, float *out_chw);
 int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw, double *abs_vor_sum_hw,
                      double *min9, double *max9, int64_t *count);

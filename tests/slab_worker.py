@@ -27,11 +27,19 @@ def main():
     for x0, _ in slab.partition(nx, world)[1:]:
         mask[x0 - 1:x0 + 1, 40:48] = True   # solids straddling every interface
         mask[x0, :2] = True
+    dwm = importlib.import_module("01-lbm-2d_b200.device_writer")
+    from oracle.writer_oracle import WriterOracle
+
+    cfg["domain_zones"]["buffer"] = 3
+    cfg["outputs"]["dataset"]["save_resolution_height"] = 29
     for arith in ("strict", "fast"):
         s = slab.SlabLBM(cfg, mask, rank=rank, world=world, device=local, arith=arith, kernel=kernel)
         s.init()
+        writer = dwm.DeviceLBMCaseWriter(os.path.join("/tmp", f"slab_case_{rank}.h5"), cfg, nx, ny, solver=s)
         for n in (1, 10, 49):
             s.run_step(n)
+            writer.append_from_solver(s)
+        exported = writer.finalize()
         fields = {nm: s.gather(getattr(s.solver, nm).to_numpy()) for nm in ("f_old", "f_new", "rho", "vel")}
         fields["moments"] = s.gather(s.get_moments_numpy())
         force, maxv = s.get_force(), s.get_max_velocity()
@@ -39,7 +47,19 @@ def main():
         if rank == 0:
             ref = OracleLBMC(cfg, mask)
             ref.init()
-            ref.run_step(60)
+            wo = WriterOracle(cfg, nx, ny)
+            for n in (1, 10, 49):
+                ref.run_step(n)
+                wo.append(ref.get_moments_numpy())
+            want_export = wo.finalize()
+            for key in ("turbulence", "mean_vel_field", "mean_vel_sq_field", "sum_vor"):
+                if arith == "strict":
+                    assert np.array_equal(exported[key], want_export[key]), ("export", key)
+                else:
+                    assert np.abs(exported[key] - want_export[key]).max() <= 1e-5 * max(1.0, np.abs(want_export[key]).max()), ("export", key)
+            if arith == "strict":
+                assert np.array_equal(writer.attrs["stats_min"], want_export["stats_min"])
+                assert np.array_equal(writer.attrs["stats_max"], want_export["stats_max"])
             want = dict(f_old=ref.f_old, f_new=ref.f_new, rho=ref.rho, vel=ref.vel, moments=ref.get_moments_numpy())
             F, S = force_f64(ref.f_new, ref.mask)
             if arith == "strict":
