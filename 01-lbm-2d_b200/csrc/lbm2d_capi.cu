@@ -200,7 +200,6 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.ny = s->ny;
     a.pitch = s->pitch;
     a.nseg = s->nseg;
-    a.n_items = s->n_items;
     a.x_off = s->x_off;
     a.west_ring = s->west_ring;
     a.east_ring = s->east_ring;

@@ -38,7 +38,7 @@ struct StepArgs {
     float *rho, *ux, *uy;           // macroscopic planes (written by EMIT steps)
     unsigned *maxv_bits;            // max(ux^2+uy^2) as ordered uint; [1] = NaN flag
     long long plane;                // floats per plane = nx_local * pitch
-    int nx_local, ny, pitch, nseg, n_items;
+    int nx_local, ny, pitch, nseg;
     int x_off;                      // global x of local column 0
     int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
     int warmup;

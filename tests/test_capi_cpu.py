@@ -38,6 +38,30 @@ def test_library_is_sm100a_only_and_has_no_cpu_path():
     assert archs == {"sm_100a"}, archs
 
 
+def test_sass_shows_the_blackwell_paths_that_are_claimed():
+    """TMA variant: UTMALDG / UTMASTG + mbarrier (SYNCS); async variant: LDGSTS; default kernel: 64-bit L1-bypassing
+    loads, warp shuffles, no local memory; PDL: ACQBULK / griddepcontrol lowered into the step kernel."""
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = {}
+    cur = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur and "/*" in line:
+            funcs[cur].append(line)
+    def body(substr):
+        names = [n for n in funcs if substr in n]
+        assert names, substr
+        return "\n".join(funcs[names[0]])
+    tma = body("step_tma_kernelILb0ELb0E")
+    assert "UTMALDG" in tma and "UTMASTG" in tma and "SYNCS" in tma
+    assert "LDGSTS" in body("step_async_kernelILb0ELb0E")
+    hot = body("step_kernelILb0ELb0ELi2E")
+    assert "LDG.E.64.STRONG.GPU" in hot and "SHFL" in hot and "STG.E.64" in hot
+    assert "STL" not in hot and "LDL" not in hot, "the default step kernel must not touch local memory"
+
+
 def test_struct_layout_matches_c(tmp_path):
     """Compile a tiny C program against the header and compare sizeof / offsetof with ctypes."""
     src = tmp_path / "layout.c"
