@@ -137,6 +137,7 @@ def run_reference(args):
         return
     cfg, mask = build_workload(args.workload, 1)
     nx, ny = cfg["simulation"]["nx"], cfg["simulation"]["ny"]
+    nx_full = nx
     sample = f"{args.warmup}+{args.steps} full-grid steps of {nx}x{ny}"
     from oracle import lbm_oracle_c
 
@@ -166,7 +167,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "grid": [nx, ny], "sample": sample},
+        "config": {
+            "workload": f"{args.workload} {nx_full}x{ny} (BASELINE configs[2] per GPU), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
+            "grid": [nx, ny], "parallelism": f"host CPU, {cores} OpenMP threads (the reference's three-pass step, C port)",
+            "sample": sample, "arith": "strict fp32 (reference evaluation order)",
+        },
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
