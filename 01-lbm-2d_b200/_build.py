@@ -44,7 +44,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lbm2d_async.cuh"
@@ -121,6 +122,8 @@ struct LbmSolver {
     float *force_out = nullptr;
     float *staging = nullptr;
     size_t staging_floats = 0;
+    char *pinned[2] = {nullptr, nullptr};   // host staging of the large device -> host getters
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     int64_t steps_done = 0;
     int64_t launches = 0;
     bool inited = false;
@@ -138,6 +141,10 @@ struct LbmSolver {
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
                           (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount})
             if (ptr) cudaFree(ptr);
+        for (int i = 0; i < 2; ++i) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -153,6 +160,47 @@ int ensure_staging(LbmSolver *s, size_t floats) {
     s->staging_floats = 0;
     CUDA_TRY(cudaMalloc(&s->staging, floats * sizeof(float)));
     s->staging_floats = floats;
+    return LBM_OK;
+}
+
+// Device -> caller-owned host array.  The reference hands out FRESH numpy arrays (they are queued to the writer
+// thread), so the destination is pageable and untouched: a plain cudaMemcpy runs at ~5 GB/s there (page faults +
+// the driver's own staging).  Large copies therefore go through two pinned chunks: the DMA of chunk i+1 overlaps
+// a multi-threaded copy (and first touch) of chunk i into the caller's array.
+constexpr size_t kPinChunk = 32u << 20;
+int d2h(LbmSolver *s, void *host, const void *dev, size_t bytes) {
+    if (bytes < 2 * kPinChunk) {
+        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return LBM_OK;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!s->pinned[i]) CUDA_TRY(cudaHostAlloc((void **)&s->pinned[i], kPinChunk, cudaHostAllocDefault));
+        if (!s->pin_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&s->pin_ev[i], cudaEventDisableTiming));
+    }
+    const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    auto scatter = [&](const char *src, char *dst, size_t n) {
+        std::vector<std::thread> pool;
+        const size_t per = (n / nthreads + 4095) / 4096 * 4096;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const size_t lo = std::min(n, (size_t)t * per), hi = std::min(n, lo + per);
+            if (hi > lo) pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
+        }
+        for (auto &th : pool) th.join();
+    };
+    const size_t nchunks = (bytes + kPinChunk - 1) / kPinChunk;
+    for (size_t i = 0; i <= nchunks; ++i) {
+        if (i < nchunks) {
+            const size_t off = i * kPinChunk, n = std::min(kPinChunk, bytes - off);
+            CUDA_TRY(cudaMemcpyAsync(s->pinned[i & 1], (const char *)dev + off, n, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaEventRecord(s->pin_ev[i & 1], s->stream));
+        }
+        if (i > 0) {
+            const size_t j = i - 1, off = j * kPinChunk, n = std::min(kPinChunk, bytes - off);
+            CUDA_TRY(cudaEventSynchronize(s->pin_ev[j & 1]));
+            scatter(s->pinned[j & 1], (char *)host + off, n);
+        }
+    }
     return LBM_OK;
 }
 
@@ -792,9 +840,7 @@ static int get_planes(LbmHandle h, const float *p0, const float *p1, int nch, fl
     lbm::pack_planes_kernel<<<grid, 128, 0, h->stream>>>(p0, p1, nch, h->own0, h->ny, h->pitch, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return d2h(h, out, h->staging, n * sizeof(float));
 }
 
 int lbm_get_vel(LbmHandle h, float *out) { return h ? get_planes(h, h->ux, h->uy, 2, out) : fail(LBM_ERR_INVALID, "null handle"); }
@@ -809,9 +855,7 @@ int lbm_get_mask(LbmHandle h, float *out) {
     lbm::mask_to_float_kernel<<<grid, 128, 0, h->stream>>>(h->code, h->own0, h->ny, h->pitch, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return d2h(h, out, h->staging, n * sizeof(float));
 }
 
 static int export9(LbmHandle h, int mode, float *out) {
@@ -824,9 +868,7 @@ static int export9(LbmHandle h, int mode, float *out) {
     lbm::export9_kernel<<<grid, 128, 0, h->stream>>>(a, mode, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    CUDA_TRY(cudaMemcpyAsync(out, h->staging, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return d2h(h, out, h->staging, n * sizeof(float));
 }
 
 int lbm_get_moments(LbmHandle h, float *out) { return export9(h, 0, out); }
