@@ -2,7 +2,9 @@
 //
 // Layout in HBM: 9 SoA planes per buffer, each (nx_local, pitch) with y fastest and
 // pitch = round_up(ny, 32) floats, so every column starts on a 128-byte line and a warp's
-// float4 accesses are full, aligned lines.  Two buffers (src/dst) swap roles every step.
+// vector accesses are full, aligned lines.  Two buffers (src/dst) swap roles every step.
+// Variants: step_kernel (register, default; this file), step_tma_kernel (lbm2d_tma.cuh),
+// step_async_kernel (lbm2d_async.cuh).
 #pragma once
 #include "lbm2d_device.cuh"
 
@@ -48,11 +50,6 @@ struct StepArgs {
     const RingCtx *ring;            // rare-path context in global memory (dst-specific)
     Physics phys;
 };
-
-__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
-    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
-}
 
 __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
     return __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy));
