@@ -85,7 +85,7 @@ class ClockSampler:
         sm, mx, reasons = [], None, set()
         rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 - 0.02 <= t <= (self.t1 or t) + 0.05)]
         where = "timed region"
-        if not rows:  # the timed region was shorter than nvidia-smi's sampling period
+        if len(rows) < 3:  # the timed region was shorter than a few nvidia-smi sampling periods
             rows, where = [r for (_, r) in self.rows], "warm-up + timed region"
         for r in rows:
             try:
@@ -335,8 +335,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank", "random"])
     ap.add_argument("--grid", default=None, help="NXxNY: urban-style obstacles on a custom grid (experiments)")
