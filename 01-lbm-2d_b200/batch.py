@@ -7,6 +7,12 @@ through the reference's run loop (`simulation_ops.run_simulation_loop`) with the
 writes its own shard `sim_results.rank{r}.json`; rank 0 merges the shards after a barrier -- no shared
 file is ever written by two processes.  There is no data-path collective: the cases are independent.
 
+Resume semantics are the reference's (`batch_run.py:78-116, 219-351`): a case recorded as `Success` or
+`Failed` is skipped, one left `Running` by a crashed session is retried; `Running` is written BEFORE a
+case starts; a case whose run loop does not end in `Success` is recorded as `Failed` with its reason and
+its output file is removed (`case_executor.py:105-107, 151-160`); `max_success` stops a rank once the
+successes of earlier sessions plus its share of the new ones reach the quota.
+
     torchrun --nproc-per-node 8 01-lbm-2d_b200/batch.py --sweep 64 --out outputs/sweep
 """
 from __future__ import annotations
@@ -24,46 +30,140 @@ def shard(names, rank, world):
     return sorted(names)[rank::world]
 
 
-def merge_shards(out_dir, world):
+def merge_shards(out_dir, world=None, remove=False):
+    """Fold every rank shard into sim_results.json (atomic replace).  `remove`: delete the shards afterwards --
+    rank 0 does this at the start of a session (`consolidate`), before any rank writes a new shard."""
     merged = {}
-    for r in range(world):
-        path = os.path.join(out_dir, f"sim_results.rank{r}.json")
-        if os.path.exists(path):
+    try:   # records of earlier sessions stay unless this session re-ran the case
+        with open(os.path.join(out_dir, "sim_results.json")) as f:
+            merged.update(json.load(f))
+    except (OSError, ValueError):
+        pass
+    for path in _shard_files(out_dir):   # every shard present (an earlier session may have used more ranks)
+        try:
             with open(path) as f:
-                merged.update(json.load(f))
+                for name, rec in json.load(f).items():
+                    if not (merged.get(name, {}).get("status") == "Success" and rec.get("status") != "Success"):
+                        merged[name] = rec
+        except (OSError, ValueError):
+            continue
     tmp = os.path.join(out_dir, "sim_results.json.tmp")
     with open(tmp, "w") as f:
         json.dump(dict(sorted(merged.items())), f, indent=2)
     os.replace(tmp, os.path.join(out_dir, "sim_results.json"))  # atomic, like sim_results_io.py:55-66
+    if remove:
+        for path in _shard_files(out_dir):
+            os.remove(path)
     return merged
 
 
-def run_cases(cases, out_dir, rank=0, world=1, device=None, max_steps=None, progress=False):
-    """cases: {name: (config, mask)}.  Returns this rank's {name: result}."""
+def consolidate(out_dir):
+    """Session start, ONE process (rank 0, before the barrier that releases the others): shards left by a
+    crashed or differently sized earlier session become part of sim_results.json."""
+    os.makedirs(out_dir, exist_ok=True)
+    return merge_shards(out_dir, remove=True) if _shard_files(out_dir) else None
+
+
+def _shard_files(out_dir):
+    if not os.path.isdir(out_dir):
+        return []
+    return sorted(os.path.join(out_dir, f) for f in os.listdir(out_dir)
+                  if f.startswith("sim_results.rank") and f.endswith(".json"))
+
+
+def load_status_map(out_dir):
+    """{case: status} from sim_results.json (sim_results_io.py:117-130)."""
+    try:
+        with open(os.path.join(out_dir, "sim_results.json")) as f:
+            return {name: rec.get("status") for name, rec in json.load(f).items()}
+    except (OSError, ValueError):
+        return {}
+
+
+def resume_plan(names, status_map):
+    """(already_success, skip) as batch_run.py:78-116: Success and Failed are skipped, Running is retried."""
+    skip, ok = set(), 0
+    for name in names:
+        st = status_map.get(name)
+        if st == "Success":
+            skip.add(name)
+            ok += 1
+        elif st == "Failed":
+            skip.add(name)
+    return ok, skip
+
+
+def _gpu_runner(name, cfg, mask, out_dir, device, max_steps, progress):
+    """One case through the reference's run loop with the device-side writer."""
     pkg = importlib.import_module("01-lbm-2d_b200")
     ops = importlib.import_module("01-lbm-2d_b200.simulation_ops")
     dwm = importlib.import_module("01-lbm-2d_b200.device_writer")
+    solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, device=device)
+    try:
+        solver.init()
+        writer = dwm.DeviceLBMCaseWriter(os.path.join(out_dir, f"{name}.h5"), cfg, solver.nx, solver.ny,
+                                         mask_data=mask, solver=solver)
+        meta = ops.run_simulation_loop(cfg, solver, None, None, None, writer,
+                                       max_steps or cfg["simulation"]["max_steps"], progress=progress)
+        writer.close()
+    finally:
+        solver.close()
+    return meta
+
+
+def _remove_outputs(out_dir, name):
+    for ext in (".h5", ".npz"):   # case_executor.py:_cleanup_failed_outputs
+        try:
+            os.remove(os.path.join(out_dir, name + ext))
+        except OSError:
+            pass
+
+
+def run_cases(cases, out_dir, rank=0, world=1, device=None, max_steps=None, progress=False, *,
+              resume=True, max_success=None, runner=None):
+    """cases: {name: (config, mask)}.  Returns this rank's {name: result} (skipped cases keep their old record
+    in the merged file and are not in the returned dict)."""
+    runner = runner or _gpu_runner
     os.makedirs(out_dir, exist_ok=True)
-    results = {}
+    if world == 1:
+        consolidate(out_dir)   # with several ranks the launcher does this once, before the start barrier (main)
+    status_map = load_status_map(out_dir) if resume else {}
+    already_success, skip = resume_plan(sorted(cases), status_map)
+    quota = None
+    if max_success is not None:   # batch_run.py:201-213, 233-241; the remaining quota is split over the ranks
+        remaining = max(0, max_success - already_success)
+        quota = remaining // world + (1 if rank < remaining % world else 0)
+    shard_path = os.path.join(out_dir, f"sim_results.rank{rank}.json")
+    results, new_success = {}, 0
+
+    def flush():
+        tmp = shard_path + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(results, f, indent=2)
+        os.replace(tmp, shard_path)
+
     for name in shard(list(cases), rank, world):
+        if name in skip:
+            continue
+        if quota is not None and new_success >= quota:
+            break
         cfg, mask = cases[name]
+        results[name] = {"status": "Running", "rank": rank}   # crash-safe pre-write, batch_run.py:253-258
+        flush()
         t0 = time.perf_counter()
         try:
-            solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, device=device)
-            solver.init()
-            writer = dwm.DeviceLBMCaseWriter(os.path.join(out_dir, f"{name}.h5"), cfg, solver.nx, solver.ny,
-                                             mask_data=mask, solver=solver)
-            meta = ops.run_simulation_loop(cfg, solver, None, None, None, writer,
-                                           max_steps or cfg["simulation"]["max_steps"], progress=progress)
-            writer.close()
-            solver.close()
+            meta = dict(runner(name, cfg, mask, out_dir, device, max_steps, progress))
+            if meta.get("status") != "Success":   # case_executor.py:105-107
+                raise RuntimeError(f"Simulation failed: {meta.get('reason', meta.get('status'))}")
+            new_success += 1
         except Exception as e:  # a failed case must not take the batch down (case_executor.py:151-160)
-            meta = {"status": "Error", "reason": str(e), "final_steps": 0}
-        meta["wall_time_s"] = time.perf_counter() - t0
+            _remove_outputs(out_dir, name)
+            meta = {"status": "Failed", "reason": str(e), "final_steps": 0}
+        meta["wall_time_s"] = round(time.perf_counter() - t0, 2)
         meta["rank"] = rank
         results[name] = meta
-        with open(os.path.join(out_dir, f"sim_results.rank{rank}.json"), "w") as f:
-            json.dump(results, f, indent=2)
+        flush()
+    flush()
     return results
 
 
@@ -72,6 +172,8 @@ def main():
     ap.add_argument("--sweep", type=int, default=64, help="number of synthetic 1024x256 cases (seeds 0..N-1)")
     ap.add_argument("--out", default="gpurun_out/sweep")
     ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--max-success", type=int, default=None)
+    ap.add_argument("--no-resume", action="store_true")
     args = ap.parse_args()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -87,17 +189,25 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = {f"sweep_{s:02d}": W.sweep_case(s) for s in range(args.sweep)}
+    if rank == 0 and world > 1:
+        consolidate(args.out)
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
-    run_cases(cases, args.out, rank, world, device=local, max_steps=args.max_steps)
+    run_cases(cases, args.out, rank, world, device=local, max_steps=args.max_steps,
+              resume=not args.no_resume, max_success=args.max_success)
     if dist is not None:
         dist.barrier()
     dt = time.perf_counter() - t0
     if rank == 0:
-        merged = merge_shards(args.out, world)
+        before = load_status_map(args.out)
+        merged = merge_shards(args.out, world, remove=True)
+        ran_now = [n for n in merged if before.get(n) not in ("Success", "Failed")]   # skipped cases cost no time
         ok = sum(1 for r in merged.values() if r["status"] == "Success")
-        steps = sum(r["final_steps"] for r in merged.values())
-        print(json.dumps({"metric": "cases/hour (64 x 1024x256 sweep incl. export)", "value": len(merged) / dt * 3600,
-                          "n_gpus": world, "cases": len(merged), "success": ok, "total_steps": steps, "wall_s": dt}))
+        steps = sum(merged[n].get("final_steps", 0) for n in ran_now)
+        print(json.dumps({"metric": "cases/hour (64 x 1024x256 sweep incl. export)", "value": len(ran_now) / dt * 3600,
+                          "n_gpus": world, "cases": len(ran_now), "cases_recorded": len(merged), "success": ok,
+                          "total_steps": steps, "wall_s": dt}))
     if dist is not None:
         dist.destroy_process_group()
 
