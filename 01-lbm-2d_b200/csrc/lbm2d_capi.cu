@@ -101,6 +101,10 @@ struct LbmSolver {
     int vwidth = 4;  // cells per thread of the register variant
     bool use_async = false;
     bool use_pdl = true;
+    long long early_min_ctas = 2500;      // grids with fewer CTAs keep the plain PDL hand-over
+    int early_target = 1500;              // CTAs that may start on the progress counter (0 = early start off)
+    unsigned long long *progress = nullptr;   // device counter, see step_kernel
+    unsigned long long progress_total = 0;    // its value once every step launched so far has signalled
     int async_grid = 0;
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
@@ -139,7 +143,8 @@ struct LbmSolver {
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
-                          (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount})
+                          (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount,
+                          (void *)progress})
             if (ptr) cudaFree(ptr);
         for (int i = 0; i < 2; ++i) {
             if (pinned[i]) cudaFreeHost(pinned[i]);
@@ -258,6 +263,7 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.il_count = s->nx_local - 2;
     a.bump_ctr = 1;
     a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, s->nx_local, s->ny, a.west_ring, a.east_ring);
+    a.progress = s->progress;
     a.phys = s->phys;
     return a;
 }
@@ -527,6 +533,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     CREATE_TRY(cudaMalloc(&s->damp_y, s->pitch * sizeof(float)));
     CREATE_TRY(cudaMalloc(&s->ramp_tab, ((size_t)p.warmup_steps + 1) * sizeof(float)));
     CREATE_TRY(cudaMalloc(&s->ctr, 2 * sizeof(int)));
+    CREATE_TRY(cudaMalloc(&s->progress, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(s->progress, 0, sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&s->maxv, 2 * sizeof(unsigned)));
     CREATE_TRY(cudaMalloc(&s->force_partial, kForceBlocks * 2 * sizeof(double)));
     CREATE_TRY(cudaMalloc(&s->force_out, 2 * sizeof(float)));
@@ -610,6 +618,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         s->use_tma = p.kernel == LBM_KERNEL_TMA;
         s->use_async = p.kernel == LBM_KERNEL_ASYNC;
         s->use_pdl = !std::getenv("LBM2D_NO_PDL");
+        if (const char *e = std::getenv("LBM2D_EARLY_CTAS")) s->early_target = std::max(0, std::atoi(e));
+        if (const char *e = std::getenv("LBM2D_EARLY_MIN_CTAS")) s->early_min_ctas = std::max(0, std::atoi(e));
         if (s->use_async) {
             const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
             int per_sm = 0;
@@ -692,16 +702,36 @@ int lbm_run(LbmHandle h, int steps) {
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
     const int ncols = h->nx_local - 2;
     // grid of the register variant: x = segment blocks of a column, y (z) = columns followed by the ring rows
-    auto grid_for = [&](lbm::StepArgs &a) {
+    // `early_cols` > 0: early-start order -- the first columns, then the ring rows, then the other columns --
+    // and the rows up to two columns past the ring signal the progress counter (they are what the next
+    // step's early columns read and overwrite).  Returns the CTAs that signal per launch in `signals`.
+    auto grid_for = [&](lbm::StepArgs &a, int early_cols = 0, unsigned long long *signals = nullptr) {
         const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
         a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, h->nx_local, h->ny, a.west_ring, a.east_ring);
         const int ring_ctas = (a.n_ring + 32 * lbm::kWarpsPerBlock - 1) / (32 * lbm::kWarpsPerBlock);
-        const int rows = a.il_count + (ring_ctas + gx - 1) / gx;
+        a.ring_rows = (ring_ctas + gx - 1) / gx;
+        a.ring_row0 = early_cols > 0 ? early_cols : a.il_count;
+        a.early_rows = 0;
+        a.low_rows = early_cols > 0 ? early_cols + a.ring_rows + 2 : 0;
+        if (signals) *signals = (unsigned long long)a.low_rows * gx;
+        const int rows = a.il_count + a.ring_rows;
         return dim3(gx, std::min(rows, 65535), (rows + 65534) / 65535);
     };
+    // Early start needs PDL, one launch per step and a grid of many waves (the early columns must be a small
+    // prefix whose inputs the previous step finished long before its tail).
+    int early_cols = 0;
+    {
+        const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+        const int want = std::min((h->early_target + gx - 1) / gx, ncols / 3);
+        const bool single = !(h->comm && h->nranks > 1);
+        // below ~2 waves of CTAs the previous step's first columns are not done when its last CTAs start: the
+        // check would always fall through to the wait and the counter update would only lengthen the step
+        const long long total_ctas = (long long)ncols * gx;
+        if (h->use_pdl && single && !h->use_tma && !h->use_async && want >= 4 && total_ctas >= h->early_min_ctas) early_cols = want;
+    }
     lbm::StepArgs a_all = make_args(h);
-    const dim3 blocks_all = grid_for(a_all);
-    (void)ncols;
+    unsigned long long signals_all = 0;
+    const dim3 blocks_all = grid_for(a_all, early_cols, &signals_all);
     if (h->comm && h->nranks > 1 && h->stream_e) {  // the side stream starts behind everything already queued
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
@@ -734,6 +764,7 @@ int lbm_run(LbmHandle h, int steps) {
         const bool overlap = h->comm && h->nranks > 1 && h->nx_local >= 6 && h->stream_e;
         cudaStream_t st = h->stream;
         dim3 blocks = blocks_all;
+        a.n_ring = a_all.n_ring; a.ring_row0 = a_all.ring_row0; a.ring_rows = a_all.ring_rows; a.low_rows = a_all.low_rows;
         if (overlap) {
             // Edge columns (1 and nx_local-2) first on the side stream, halo exchange right behind them, the
             // interior on the main stream meanwhile.  edge(n) needs interior(n-1) and exchange(n-1);
@@ -770,7 +801,11 @@ int lbm_run(LbmHandle h, int steps) {
         } else {
             // PDL between consecutive plain steps of a batch (not across the max|u| memset of an EMIT step)
             const bool pdl = h->use_pdl && !overlap && !emit && it > 0;
+            // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
+            a.early_rows = (pdl && early_cols > 0) ? early_cols : 0;
+            a.progress_expected = h->progress_total;
             CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth), blocks, st, a, pdl));
+            if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;
         h->launches++;

@@ -47,6 +47,12 @@ struct StepArgs {
     int il0, il_step, il_count;     // columns of this launch: il0 + blockIdx.y * il_step, blockIdx.y < il_count
     int bump_ctr;                   // this launch advances frame_count (exactly one launch per step does)
     int n_ring;                     // ring cells handled by this launch's ring warps
+    int ring_row0, ring_rows;       // grid rows [ring_row0, ring_row0 + ring_rows) hold the ring warps, the others columns
+    // Early start (see step_kernel): rows [0, early_rows) may begin on the progress counter instead of the full
+    // completion of the previous step; rows [0, low_rows) of every step add 1 per CTA to it when done.
+    int early_rows, low_rows;
+    unsigned long long *progress;
+    unsigned long long progress_expected;   // counter value once the previous step's rows [0, low_rows) are complete
     const RingCtx *ring;            // rare-path context in global memory (dst-specific)
     Physics phys;
 };
@@ -188,22 +194,35 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 // the columns): one ring cell per lane, see above.
 template <bool STRICT, bool EMIT, int V>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
-    // Programmatic dependent launch: the next step's grid may be scheduled while this one drains, and waits
-    // here until this grid's writes are complete and visible (a no-op for ordinary launches).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows: interior columns, with the
+    // ring rows inserted at ring_row0 (after the early columns; at the end when early start is off)
+    const int row = blockIdx.y + blockIdx.z * 65535;
+    // Programmatic dependent launch: this grid is scheduled while the previous step drains, and waits here
+    // until that grid's writes are complete and visible (a no-op for ordinary launches).  Early start: the
+    // CTAs of the first columns -- the ones that get the SM slots freed during the previous step's tail --
+    // need only the previous step's first columns and ring, which finished ~190 us ago; they check a
+    // progress counter (one acquire load, no polling) and fall back to the full wait if it is not there yet.
+    if (row < a.early_rows) {
+        unsigned long long seen;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
+        if (seen < a.progress_expected) asm volatile("griddepcontrol.wait;" ::: "memory");
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     asm volatile("griddepcontrol.launch_dependents;");
-    // grid: x = blocks of segments down a column, y (+ z beyond 65535) = interior column, then ring rows
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int col = blockIdx.y + blockIdx.z * 65535;
-    if (a.bump_ctr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.ctr_out = *a.ctr_in + 1;  // ref:440
+    const int ring_rel = row - a.ring_row0;
+    const bool ring_row = ring_rel >= 0 && ring_rel < a.ring_rows;
+    const int col = ring_rel < 0 ? row : row - a.ring_rows;
+    if (a.bump_ctr && blockIdx.x == 0 && row == 0 && threadIdx.x == 0) *a.ctr_out = __ldcg(a.ctr_in) + 1;  // ref:440
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
-    if (col >= a.il_count) {
+    if (ring_row) {
         // ------------------------------- ring warps ------------------------------------------
-        const int idx = ((col - a.il_count) * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT>(a, idx, *a.ctr_in + 1, vmax, vnan);
-    } else if (seg < a.nseg) {
+        const int idx = (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT>(a, idx, __ldcg(a.ctr_in) + 1, vmax, vnan);
+    } else if (col < a.il_count && seg < a.nseg) {
         // ------------------------------- interior warps --------------------------------------
         const int il = a.il0 + col * a.il_step;                              // local column
         const int j0 = seg * (32 * V) + lane * V;
@@ -323,6 +342,13 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
             const unsigned bits = __float_as_uint(vmax);
             if (bits > *a.maxv_bits) atomicMax(a.maxv_bits, bits);
             if (any_nan) a.maxv_bits[1] = 1u;
+        }
+    }
+    if (row < a.low_rows) {   // release: this CTA's part of the low rows is complete and visible device-wide
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(a.progress, 1ULL);
         }
     }
 }

@@ -291,6 +291,35 @@ def test_full_size_8192x2048_vs_oracle_and_invariants(pkg):
     assert r.get_max_velocity() < 1e-6 and abs(float(r.rho.to_numpy().mean()) - 1.0) < 1e-6
 
 
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("nx,ny", [(8192, 2048), (2048, 8192)])
+def test_early_start_is_bit_identical_to_full_serialisation(pkg, arith, nx, ny, monkeypatch):
+    """The first columns of a step start on the progress counter while the previous step drains (step_kernel).
+    Same state, bit for bit, as with early start off and as with PDL off, over several hundred steps in uneven
+    batches (a race would show up as a difference)."""
+    cfg = make_config(nx, ny, rho_in=1.01, nu=0.007, cs=0.1, warmup=50, sponge=(64, 256, 64, 64), L=200.0)
+    rng = np.random.default_rng(3)
+    mask = np.zeros((nx, ny), bool)
+    for _ in range(40):
+        w, h = rng.integers(20, 200, 2)
+        x, y = rng.integers(0, nx - w), rng.integers(0, ny - h)   # some rectangles touch the first columns / the ring
+        mask[x:x + w, y:y + h] = True
+    outs = []
+    for env in ({}, {"LBM2D_EARLY_CTAS": "0"}, {"LBM2D_NO_PDL": "1"}):
+        for k in ("LBM2D_EARLY_CTAS", "LBM2D_NO_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=arith, kernel="register2")
+        s.init()
+        for n in (7, 200, 1, 2, 190):
+            s.run_step(n)
+        outs.append((s.f_old.to_numpy(), s.rho.to_numpy(), s.get_max_velocity(), s.step_count()))
+        s.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and outs[0][2:] == o[2:]
+
+
 # ------------------------------------------------------------------ long unsteady run: mean fields (north_star: <= 1e-3)
 def test_long_unsteady_run_mean_fields_within_1e3(pkg, tmp_path):
     """30 000 steps of an off-centre cylinder at Re ~ 100 (vortex shedding: the standard deviation of jx over the
