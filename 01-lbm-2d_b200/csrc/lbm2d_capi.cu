@@ -707,14 +707,18 @@ int lbm_run(LbmHandle h, int steps) {
     // step's early columns read and overwrite).  Returns the CTAs that signal per launch in `signals`.
     auto grid_for = [&](lbm::StepArgs &a, int early_cols = 0, unsigned long long *signals = nullptr) {
         const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+        const int G = lbm::kRingGroup;
         a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, h->nx_local, h->ny, a.west_ring, a.east_ring);
-        const int ring_ctas = (a.n_ring + 32 * lbm::kWarpsPerBlock - 1) / (32 * lbm::kWarpsPerBlock);
-        a.ring_rows = (ring_ctas + gx - 1) / gx;
-        a.ring_row0 = early_cols > 0 ? early_cols : a.il_count;
+        // rows: groups of G columns + 1 top/bottom ring row each; the W/E ring block behind the early groups
+        const int vrows = (a.il_count + G - 1) / G * (G + 1);
+        const int we_cells = a.n_ring - 2 * a.il_count;
+        const int we_ctas = (we_cells + 32 * lbm::kWarpsPerBlock - 1) / (32 * lbm::kWarpsPerBlock);
+        a.ring_rows = (we_ctas + gx - 1) / gx;
+        a.ring_row0 = early_cols > 0 ? early_cols / G * (G + 1) : vrows;
         a.early_rows = 0;
-        a.low_rows = early_cols > 0 ? early_cols + a.ring_rows + 2 : 0;
+        a.low_rows = early_cols > 0 ? a.ring_row0 + a.ring_rows + 2 : 0;
         if (signals) *signals = (unsigned long long)a.low_rows * gx;
-        const int rows = a.il_count + a.ring_rows;
+        const int rows = vrows + a.ring_rows;
         return dim3(gx, std::min(rows, 65535), (rows + 65534) / 65535);
     };
     // Early start needs PDL, one launch per step and a grid of many waves (the early columns must be a small
@@ -722,7 +726,7 @@ int lbm_run(LbmHandle h, int steps) {
     int early_cols = 0;
     {
         const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
-        const int want = std::min((h->early_target + gx - 1) / gx, ncols / 3);
+        const int want = std::min((h->early_target + gx - 1) / gx, ncols / 3) / lbm::kRingGroup * lbm::kRingGroup;  // whole groups
         const bool single = !(h->comm && h->nranks > 1);
         // below ~2 waves of CTAs the previous step's first columns are not done when its last CTAs start: the
         // check would always fall through to the wait and the counter update would only lengthen the step
@@ -802,7 +806,7 @@ int lbm_run(LbmHandle h, int steps) {
             // PDL between consecutive plain steps of a batch (not across the max|u| memset of an EMIT step)
             const bool pdl = h->use_pdl && !overlap && !emit && it > 0;
             // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
-            a.early_rows = (pdl && early_cols > 0) ? early_cols : 0;
+            a.early_rows = (pdl && early_cols > 0) ? a_all.ring_row0 : 0;
             a.progress_expected = h->progress_total;
             CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth), blocks, st, a, pdl));
             if (!overlap) h->progress_total += signals_all;
