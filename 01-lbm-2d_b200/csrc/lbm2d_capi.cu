@@ -91,6 +91,7 @@ struct LbmSolver {
     long long plane = 0;
     float *f[2] = {nullptr, nullptr};
     uint8_t *code = nullptr;
+    uint32_t *code_bits = nullptr;
     float *damp_x = nullptr, *damp_y = nullptr, *ramp_tab = nullptr;
     int *ctr = nullptr;
     float *mac = nullptr;  // rho | ux | uy, three consecutive planes (one TMA store tensor)
@@ -144,7 +145,7 @@ struct LbmSolver {
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
                           (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount,
-                          (void *)progress})
+                          (void *)progress, (void *)code_bits})
             if (ptr) cudaFree(ptr);
         for (int i = 0; i < 2; ++i) {
             if (pinned[i]) cudaFreeHost(pinned[i]);
@@ -239,6 +240,7 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.src = s->f[par];
     a.dst = s->f[par ^ 1];
     a.code = s->code;
+    a.code_bits = s->code_bits;
     a.damp_x = s->damp_x;
     a.damp_y = s->damp_y;
     a.ramp_tab = s->ramp_tab;
@@ -545,6 +547,13 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         for (int il = 0; il < s->nx_local; ++il)
             for (int j = 0; j < s->ny; ++j) code[(size_t)il * s->pitch + j] = mask_xy[(size_t)il * s->ny + j] ? 1 : 0;
     CREATE_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
+    {   // bit-packed copy for the interior warps (1/8 of the bytes per step)
+        std::vector<uint32_t> bits(((size_t)s->plane + 31) / 32 + 2, 0u);
+        for (size_t o = 0; o < (size_t)s->plane; ++o)
+            if (code[o] & 1) bits[o >> 5] |= 1u << (o & 31);
+        CREATE_TRY(cudaMalloc(&s->code_bits, bits.size() * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(s->code_bits, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
 
     // sponge tables (ref:90-94 widths are max(1, cfg))
     const int w_in = std::max(1, p.sponge_in), w_out = std::max(1, p.sponge_out);

@@ -17,7 +17,7 @@ namespace lbm {
 #define LBM_WPB 4
 #endif
 #ifndef LBM_MINB2
-#define LBM_MINB2 8
+#define LBM_MINB2 10
 #endif
 #ifndef LBM_MINB1
 #define LBM_MINB1 12
@@ -34,6 +34,7 @@ struct StepArgs {
     const float *__restrict__ src;  // 9 planes
     float *__restrict__ dst;        // 9 planes
     const uint8_t *__restrict__ code;  // cell code, bit0 = solid
+    const uint32_t *__restrict__ code_bits;  // the same bit, 32 cells per word (plane order): what the interior warps read
     const float *__restrict__ damp_x;  // [nx_local]   ref:364-370 (indexed by local column, holds the global value)
     const float *__restrict__ damp_y;  // [pitch]      ref:372-378
     const float *__restrict__ ramp_tab;  // [warmup+1]  ref:442-443
@@ -267,7 +268,10 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
         if (live) {
             dx = __ldg(a.damp_x + il);
             ldv<V>(a.damp_y + j0, dy);
-            ldcode<V>(a.code + (long long)il * pitch + j0, code);
+            // solid bits of the warp's 32 V cells = V consecutive words; a lane's V cells sit in one of them
+            const uint32_t w = __ldg(a.code_bits + (((long long)il * pitch + j0) >> 5));
+#pragma unroll
+            for (int c = 0; c < V; ++c) code[c] = (w >> ((j0 & 31) + c)) & 1u;
         }
         float fin[V][9];
 #pragma unroll
