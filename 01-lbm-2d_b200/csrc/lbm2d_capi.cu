@@ -93,6 +93,7 @@ struct LbmSolver {
     float *f[2] = {nullptr, nullptr};
     uint8_t *code = nullptr;
     uint32_t *code_bits = nullptr;
+    uint8_t *links8 = nullptr;            // bounce-back mode only
     float *damp_x = nullptr, *damp_y = nullptr, *ramp_tab = nullptr;
     int *ctr = nullptr;
     float *mac = nullptr;  // rho | ux | uy, three consecutive planes (one TMA store tensor)
@@ -146,7 +147,7 @@ struct LbmSolver {
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
                           (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount,
-                          (void *)progress, (void *)code_bits})
+                          (void *)progress, (void *)code_bits, (void *)links8})
             if (ptr) cudaFree(ptr);
         for (int i = 0; i < 2; ++i) {
             if (pinned[i]) cudaFreeHost(pinned[i]);
@@ -247,6 +248,7 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.dst = s->f[par ^ 1];
     a.code = s->code;
     a.code_bits = s->code_bits;
+    a.links8 = s->links8;
     a.damp_x = s->damp_x;
     a.damp_y = s->damp_y;
     a.ramp_tab = s->ramp_tab;
@@ -415,7 +417,10 @@ int exchange_halos(LbmSolver *s, float *buf, cudaStream_t st) {
 }
 
 typedef void (*StepFn)(const lbm::StepArgs);
-StepFn step_fn(bool strict, bool emit, int v) {
+StepFn step_fn(bool strict, bool emit, int v, bool bb = false) {
+    if (bb)   // bounce-back obstacle mode: 2 cells per thread only
+        return strict ? (emit ? (StepFn)lbm::step_kernel<true, true, 2, true> : (StepFn)lbm::step_kernel<true, false, 2, true>)
+                      : (emit ? (StepFn)lbm::step_kernel<false, true, 2, true> : (StepFn)lbm::step_kernel<false, false, 2, true>);
 #define LBM_PICK(S, E) (v == 4 ? (StepFn)lbm::step_kernel<S, E, 4> : v == 2 ? (StepFn)lbm::step_kernel<S, E, 2> : (StepFn)lbm::step_kernel<S, E, 1>)
     return strict ? (emit ? LBM_PICK(true, true) : LBM_PICK(true, false)) : (emit ? LBM_PICK(false, true) : LBM_PICK(false, false));
 #undef LBM_PICK
@@ -465,7 +470,11 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     if (p.nx_global < 3) return fail(LBM_ERR_INVALID, "need nx_global >= 3");
     if (p.slab_x0 < 0 || p.slab_x0 + p.nx > p.nx_global) return fail(LBM_ERR_INVALID, "slab outside the global domain");
     if (p.warmup_steps < 0) return fail(LBM_ERR_INVALID, "warmup_steps < 0");
-    if (p.obstacle_mode != LBM_OBSTACLE_REFILL) return fail(LBM_ERR_INVALID, "unsupported obstacle_mode");
+    if (p.obstacle_mode != LBM_OBSTACLE_REFILL && p.obstacle_mode != LBM_OBSTACLE_BOUNCE_BACK)
+        return fail(LBM_ERR_INVALID, "unsupported obstacle_mode");
+    if (p.obstacle_mode == LBM_OBSTACLE_BOUNCE_BACK &&
+        ((p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER2) || (p.nx_global > 0 && p.nx_global != p.nx)))
+        return fail(LBM_ERR_INVALID, "obstacle_mode bounce-back: single GPU and the default kernel only");
     if (p.arith != LBM_ARITH_FAST && p.arith != LBM_ARITH_STRICT) return fail(LBM_ERR_INVALID, "unsupported arith");
     if (p.warmup_steps > (1 << 26)) return fail(LBM_ERR_INVALID, "warmup_steps too large for the ramp table");
 
@@ -553,6 +562,21 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         for (int il = 0; il < s->nx_local; ++il)
             for (int j = 0; j < s->ny; ++j) code[(size_t)il * s->pitch + j] = mask_xy[(size_t)il * s->ny + j] ? 1 : 0;
     CREATE_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
+    if (p.obstacle_mode == LBM_OBSTACLE_BOUNCE_BACK) {   // solid upstream neighbours of every fluid cell
+        static const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+        std::vector<uint8_t> links((size_t)s->plane + 64, 0);
+        for (int il = 1; il < s->nx_local - 1; ++il)
+            for (int j = 1; j < s->ny - 1; ++j) {
+                const size_t o = (size_t)il * s->pitch + j;
+                if (code[o] & 1) continue;
+                uint8_t l = 0;
+                for (int k = 1; k < 9; ++k)
+                    if (code[(size_t)(il - ex[k]) * s->pitch + (j - ey[k])] & 1) l |= (uint8_t)(1u << (k - 1));
+                links[o] = l;
+            }
+        CREATE_TRY(cudaMalloc(&s->links8, links.size()));
+        CREATE_TRY(cudaMemcpy(s->links8, links.data(), links.size(), cudaMemcpyHostToDevice));
+    }
     {   // bit-packed copy for the interior warps (1/8 of the bytes per step)
         std::vector<uint32_t> bits(((size_t)s->plane + 31) / 32 + 2, 0u);
         for (size_t o = 0; o < (size_t)s->plane; ++o)
@@ -823,7 +847,7 @@ int lbm_run(LbmHandle h, int steps) {
             // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
             a.early_rows = (pdl && early_cols > 0) ? a_all.ring_row0 : 0;
             a.progress_expected = h->progress_total;
-            CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth), blocks, st, a, pdl));
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth, h->links8 != nullptr), blocks, st, a, pdl));
             if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;

@@ -34,6 +34,7 @@ struct StepArgs {
     const float *__restrict__ src;  // 9 planes
     float *__restrict__ dst;        // 9 planes
     const uint8_t *__restrict__ code;  // cell code, bit0 = solid
+    const uint8_t *__restrict__ links8;  // bounce-back mode only: bit k-1 set = the upstream neighbour i - e_k of this FLUID cell is solid
     const uint32_t *__restrict__ code_bits;  // the same bit, 32 cells per word (plane order): what the interior warps read
     const float *__restrict__ damp_x;  // [nx_local]   ref:364-370 (indexed by local column, holds the global value)
     const float *__restrict__ damp_y;  // [pitch]      ref:372-378
@@ -107,6 +108,16 @@ __device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) 
     else o[0] = __ldg(p);
 }
 
+// Half-way bounce-back (optional obstacle mode, not the reference's): a population whose upstream neighbour is
+// solid is replaced by the cell's own post-collision population of the opposite direction from the
+// previous step, f_k(x, t+1) = f*_opp(k)(x, t); the source buffer holds exactly those values.
+__device__ constexpr int kOpp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+__device__ __forceinline__ void bounce_back(const StepArgs &a, unsigned links, long long o, float (&fin)[9]) {
+#pragma unroll
+    for (int k = 1; k < 9; ++k)
+        if ((links >> (k - 1)) & 1u) fin[k] = LBM_LD(a.src + kOpp[k] * a.plane + o);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ring warps.  Every boundary-ring cell is a function of ONE adjacent interior cell's fresh, un-refilled
 // state (corners chain through the W/E cell).  Instead of making the interior thread that
@@ -128,7 +139,7 @@ __host__ __device__ inline int ring_cell_count(int il0, int il_step, int il_coun
     return 2 * il_count + (w ? ny : 0) + (e ? ny : 0);   // (ny - 2) column cells + 2 corners per side
 }
 
-template <bool STRICT, bool EMIT>
+template <bool STRICT, bool EMIT, bool BB>
 __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_fc, float &vmax, int &vnan) {
     const int ny = a.ny, pitch = a.pitch, n = a.il_count;
     const long long plane = a.plane;
@@ -156,6 +167,11 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
     float fin[9], g[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) fin[k] = LBM_LD(a.src + k * plane + (long long)(ilo - kEx[k]) * pitch + (jo - kEy[k]));
+    if (BB) {
+        const long long oo = (long long)ilo * pitch + jo;
+        const unsigned links = __ldg(a.links8 + oo);
+        if (links) bounce_back(a, links, oo, fin);
+    }
     const float damp = fmaxf(__ldg(a.damp_x + ilo), __ldg(a.damp_y + jo));
     if (STRICT) collide_strict(a.phys, fin, damp, g);
     else collide_fast(a.phys, fin, damp, g);
@@ -174,7 +190,10 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
         r = cr;
     }
     const long long o = (long long)ilr * pitch + jr;
-    if (__ldg(a.code + o) & 1) refill(r);   // ref:452-455 also resets solid ring cells
+    if (__ldg(a.code + o) & 1) {   // ref:452-455 also resets solid ring cells
+        if (BB) cell_rest(r);      // bounce-back mode: solids are frozen at rest
+        else refill(r);
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.dst[k * plane + o] = r.f[k];
     if (EMIT) {
@@ -195,7 +214,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 // pull in y comes from the neighbouring lane by warp shuffle with one extra scalar load at each end of
 // the segment, all issued before first use; no boundary code at all.  Ring warps (blockIdx.y beyond
 // the columns): one ring cell per lane, see above.
-template <bool STRICT, bool EMIT, int V>
+template <bool STRICT, bool EMIT, int V, bool BB = false>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
     // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows: interior columns, with the
     // ring rows inserted at ring_row0 (after the early columns; at the end when early start is off)
@@ -232,12 +251,12 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
     if (we_row) {
         // ------------------------------- ring warps: W / E columns and corners -----------------
         const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT>(a, idx, __ldcg(a.ctr_in) + 1, vmax, vnan);
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, __ldcg(a.ctr_in) + 1, vmax, vnan);
     } else if (tb_row) {
         // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
         const int c = grp * kRingGroup + lane;
         if (blockIdx.x == 0 && threadIdx.x < 64 && c < a.il_count)
-            ring_cell<STRICT, EMIT>(a, (threadIdx.x >> 5) * a.il_count + c, __ldcg(a.ctr_in) + 1, vmax, vnan);
+            ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, __ldcg(a.ctr_in) + 1, vmax, vnan);
     } else if (col < a.il_count && seg < a.nseg) {
         // ------------------------------- interior warps --------------------------------------
         const int il = a.il0 + col * a.il_step;                              // local column
@@ -262,9 +281,9 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
         const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
         float dx = 0.f;
         float dy[V];
-        unsigned char code[V];
+        unsigned char code[V], links[V];
 #pragma unroll
-        for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; }
+        for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; links[c] = 0; }
         if (live) {
             dx = __ldg(a.damp_x + il);
             ldv<V>(a.damp_y + j0, dy);
@@ -272,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
             const uint32_t w = __ldg(a.code_bits + (((long long)il * pitch + j0) >> 5));
 #pragma unroll
             for (int c = 0; c < V; ++c) code[c] = (w >> ((j0 & 31) + c)) & 1u;
+            if (BB) ldcode<V>(a.links8 + (long long)il * pitch + j0, links);
         }
         float fin[V][9];
 #pragma unroll
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
                 all_interior &= interior[c];
                 any_interior |= interior[c];
                 const float damp = fmaxf(dx, dy[c]);
+                if (BB && links[c]) bounce_back(a, links[c], (long long)il * pitch + j0 + c, fin[c]);
 #ifdef LBM_NOMATH   // experiment: pure streaming bound of this access pattern
 #pragma unroll
                 for (int k = 0; k < 9; ++k) g[c][k] = fin[c][k] + damp;
@@ -313,8 +334,9 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
 #endif
                 rho[c] = ux[c] = uy[c] = 0.0f;
                 if (EMIT || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
-                if (code[c] & 1) {  // obstacle refill, ref:452-455
+                if (code[c] & 1) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
                     ux[c] = 0.0f; uy[c] = 0.0f;
+                    if (BB) rho[c] = 1.0f;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
                 }

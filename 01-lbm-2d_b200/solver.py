@@ -27,14 +27,17 @@ class _FieldShim:
 
 
 class LBM2D_MRT_LES:
-    def __init__(self, config, mask_data=None, *, arith="fast", kernel="auto", device=None, slab=None):
+    def __init__(self, config, mask_data=None, *, arith="fast", kernel="auto", device=None, slab=None,
+                 obstacle_mode="refill"):
         """ref:13-29.  `config` is the per-case YAML dict; missing keys raise KeyError like the
         reference.  `mask_data`: bool/float (nx, ny), True/1 = solid, None = all fluid (ref:107-111).
 
         Extensions (keyword-only, absent from the reference): `arith` = "fast" | "strict"
         (strict is bit-identical to the fp32 oracle), `kernel` = "auto" | "register" | "tma",
         `device` = CUDA ordinal, `slab` =
-        (x0, nx_owned) to own a column range of a larger global domain (multi-GPU).
+        (x0, nx_owned) to own a column range of a larger global domain (multi-GPU), `obstacle_mode` =
+        "refill" (the reference's wet-node refill, ref:452-455) | "bounce_back" (half-way bounce-back on the
+        solid links, solids frozen at rest -- not reference behaviour; single GPU, default kernel).
         """
         self.config = config
         self._init_params()
@@ -66,7 +69,7 @@ class LBM2D_MRT_LES:
             p.bc_value[d][1] = float(bc_value[d][1])
         p.arith = _capi.ARITH[arith]
         p.kernel = _capi.KERNEL[kernel]
-        p.obstacle_mode = 0
+        p.obstacle_mode = {"refill": 0, "bounce_back": 1}[obstacle_mode]
         p.device = -1 if device is None else int(device)
         p.nx_global, p.slab_x0 = self.nx, x0
         self._params = p

@@ -56,7 +56,9 @@ typedef enum {
 } LbmKernel;
 
 typedef enum {
-    LBM_OBSTACLE_REFILL = 0 /* wet-node equilibrium refill, ref:452-455 (what the reference does) */
+    LBM_OBSTACLE_REFILL = 0,     /* wet-node equilibrium refill, ref:452-455 (what the reference does; parity mode) */
+    LBM_OBSTACLE_BOUNCE_BACK = 1 /* half-way bounce-back on solid links, solids frozen at rest: NOT reference behaviour,
+                                    optional (single GPU, default kernel); checked against oracle/lbm_oracle_np.py */
 } LbmObstacleMode;
 
 /*

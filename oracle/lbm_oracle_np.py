@@ -33,6 +33,7 @@ E = np.array(
     [[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1]],
     dtype=np.int64,
 )
+OPP = (0, 3, 4, 1, 2, 7, 8, 5, 6)  # index of -e_k (the inv_k column of ref:597-607)
 # Lallemand-Luo transform, ref:167-180
 M_NP = np.array(
     [
@@ -89,12 +90,21 @@ def ramp_value(frame_count: int, warmup_steps, F=np.float32):
 class OracleLBM:
     """Same surface as the reference class (ref:10), state held in numpy arrays."""
 
-    def __init__(self, config, mask_data=None, dtype=np.float32, exact_inv_m=False, slab=None):
-        """`slab=(x0, nx_owned)`: hold only global columns [x0, x0+nx_owned) plus one halo column on every
+    def __init__(self, config, mask_data=None, dtype=np.float32, exact_inv_m=False, slab=None, obstacle_mode="refill"):
+        """`obstacle_mode`: "refill" is the reference (ref:452-455).  "bounce_back" is NOT reference behaviour: it
+        is the optional half-way bounce-back mode the B200 build offers next to it -- a fluid
+        cell whose upstream neighbour i - e_k is solid takes its own post-collision f_opp(k) of the previous
+        step instead of pulling, and solid cells are frozen at rest (rho = 1, u = 0) -- restated here so that
+        the CUDA path has a checker for that mode too.
+
+        `slab=(x0, nx_owned)`: hold only global columns [x0, x0+nx_owned) plus one halo column on every
         side that is not a domain boundary; `halo_pack` / `halo_unpack` move the populations that
         cross an interface.  A set of slab oracles exchanging halos every step equals the monolithic oracle
         bit for bit (tests/test_slab_cpu.py) -- that is the property the multi-GPU path relies on."""
         self.config = config
+        if obstacle_mode not in ("refill", "bounce_back"):
+            raise ValueError(f"obstacle_mode {obstacle_mode!r}")
+        self.obstacle_mode = obstacle_mode
         self.F = F = np.dtype(dtype).type
         sim = config["simulation"]  # ref:33-44 (strict indexing: KeyError on missing keys)
         self.name = sim["name"]
@@ -204,6 +214,12 @@ class OracleLBM:
         nx, ny = self.nx_local, self.ny
         fo = self.f_old
         f = [fo[1 - E[k, 0] : nx - 1 - E[k, 0], 1 - E[k, 1] : ny - 1 - E[k, 1], k] for k in range(9)]
+        if self.obstacle_mode == "bounce_back":   # extension, see __init__
+            solid = self.mask == 1.0
+            own_fluid = ~solid[1 : nx - 1, 1 : ny - 1]
+            for k in range(1, 9):
+                nb_solid = solid[1 - E[k, 0] : nx - 1 - E[k, 0], 1 - E[k, 1] : ny - 1 - E[k, 1]]
+                f[k] = np.where(nb_solid & own_fluid, fo[1 : nx - 1, 1 : ny - 1, OPP[k]], f[k])
         with np.errstate(all="ignore"):
             m = []
             for r in range(9):
@@ -375,6 +391,8 @@ class OracleLBM:
         solid[: self._own0] = False                       # halo columns belong to the neighbour
         solid[self._own0 + self._nx_owned:] = False
         self.vel[solid] = 0
+        if self.obstacle_mode == "bounce_back":   # frozen at rest
+            self.rho[solid] = 1
         self.f_old[solid] = self._f_eq(self.rho[solid], self.vel[solid])
 
     # ------------------------------------------------------------------ slab halos

@@ -5,7 +5,7 @@ import pytest
 
 from helpers import cylinder_mask, golden_cases, load_golden, make_config, random_blocks_mask, rel_linf
 from oracle.lbm_oracle_c import OracleLBMC
-from oracle.lbm_oracle_np import M_NP, OracleLBM, inv_m, ramp_value
+from oracle.lbm_oracle_np import E, M_NP, OracleLBM, inv_m, ramp_value
 
 FIELDS = ("f_old", "f_new", "rho", "vel")
 
@@ -182,3 +182,32 @@ def test_c_and_numpy_oracles_agree_on_random_small_configs():
         for nm in FIELDS:
             assert np.array_equal(getattr(a, nm), getattr(b, nm), equal_nan=True), (trial, nm)
         assert np.array_equal(a.get_moments_numpy(), b.get_moments_numpy(), equal_nan=True), trial
+
+
+def test_bounce_back_extension_of_the_numpy_oracle():
+    """`obstacle_mode="bounce_back"` is NOT reference behaviour (ref:452-455 refills); it is the checker of the CUDA
+    build's optional mode.  Properties of the rule itself: OPP is the index of -e_k; with no solids it changes nothing;
+    in a pressure-driven channel between solid slabs the no-slip wall sits half-way between the last fluid and the
+    first solid node (y = 2.5 / ny - 3.5 for three solid rows per side), where the reference's refill gives 2.2."""
+    from oracle.lbm_oracle_np import OPP
+    assert all((E[OPP[k]] == -E[k]).all() for k in range(9))
+    cfg = make_config(20, 12, rho_in=1.01, warmup=3)
+    a, b = OracleLBM(cfg, None), OracleLBM(cfg, None, obstacle_mode="bounce_back")
+    a.init(), b.init()
+    a.run_step(20), b.run_step(20)
+    assert np.array_equal(a.f_old, b.f_old)
+    nx, ny = 24, 22
+    cfg = make_config(nx, ny, rho_in=1.0006, rho_out=1.0, nu=0.1, cs=0.0, warmup=0, sponge=(0, 0, 0, 0), strength=0.0)
+    mask = np.zeros((nx, ny), bool)
+    mask[:, :3] = True
+    mask[:, -3:] = True
+    roots = {}
+    for mode in ("bounce_back", "refill"):
+        o = OracleLBM(cfg, mask, dtype=np.float64, obstacle_mode=mode)
+        o.init()
+        o.run_step(2500)
+        roots[mode] = np.sort(np.roots(np.polyfit(np.arange(3, ny - 3), o.vel[nx // 2, 3:ny - 3, 0], 2)))
+        if mode == "bounce_back":
+            assert np.all(o.rho[mask] == 1.0) and np.all(o.vel[mask] == 0.0)
+    assert np.abs(roots["bounce_back"] - [2.5, ny - 3.5]).max() < 0.03
+    assert np.abs(roots["refill"] - [2.5, ny - 3.5]).max() > 0.2
