@@ -95,3 +95,32 @@ def test_unmerged_shards_of_a_crashed_session_are_carried_over(tmp_path):
     batch.run_cases(cases, str(tmp_path), rank=0, world=1, runner=_fake_runner(log))  # new session consolidates first
     assert log == ["c1", "c3"]
     assert set(batch.merge_shards(str(tmp_path), 1)) == set(cases)
+
+
+def test_concurrent_cases_overlap_and_keep_the_bookkeeping(tmp_path):
+    import threading
+    import time
+
+    cases = {f"c{i:02d}": ({}, None) for i in range(12)}
+    live, peak, lock = [0], [0], threading.Lock()
+
+    def runner(name, cfg, mask, out_dir, device, max_steps, progress):
+        with lock:
+            live[0] += 1
+            peak[0] = max(peak[0], live[0])
+        time.sleep(0.05)
+        with lock:
+            live[0] -= 1
+        if name == "c05":
+            raise RuntimeError("boom")
+        return {"status": "Success", "final_steps": 3}
+
+    res = batch.run_cases(cases, str(tmp_path), runner=runner, concurrency=4)
+    assert peak[0] == 4 and set(res) == set(cases)
+    assert res["c05"]["status"] == "Failed" and sum(v["status"] == "Success" for v in res.values()) == 11
+    on_disk = json.loads((tmp_path / "sim_results.rank0.json").read_text())
+    assert {k: v["status"] for k, v in on_disk.items()} == {k: v["status"] for k, v in res.items()}
+    # quota under concurrency: never more successes than asked for, and failures do not eat the quota
+    out2 = tmp_path / "q"
+    res2 = batch.run_cases(cases, str(out2), runner=runner, concurrency=4, max_success=7)
+    assert sum(v["status"] == "Success" for v in res2.values()) == 7
