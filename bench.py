@@ -148,8 +148,8 @@ def run_reference(args):
     t0 = time.perf_counter()
     o.run_step(1)
     t1 = time.perf_counter() - t0
-    if t1 * (args.steps + args.warmup) > 240.0:  # keep the run within a few minutes: crop the slab in x
-        frac = max(1, int(240.0 / (t1 * (args.steps + args.warmup)) * nx) // 64 * 64)
+    if t1 * (args.steps + args.warmup) > 120.0:  # keep the run within a few minutes: crop the slab in x
+        frac = max(1, int(120.0 / (t1 * (args.steps + args.warmup)) * nx) // 64 * 64)
         nx_s = max(256, frac)
         cfg = json.loads(json.dumps(cfg))
         cfg["simulation"]["nx"] = nx_s

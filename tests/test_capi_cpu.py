@@ -60,6 +60,10 @@ def test_sass_shows_the_blackwell_paths_that_are_claimed():
     hot = body("step_kernelILb0ELb0ELi2E")
     assert "LDG.E.64.STRONG.GPU" in hot and "SHFL" in hot and "STG.E.64" in hot
     assert "STL" not in hot and "LDL" not in hot, "the default step kernel must not touch local memory"
+    # programmatic dependent launch (griddepcontrol.wait) and the early-start progress counter (acquire load that
+    # invalidates L1, release = barrier + fence + 64-bit reduction)
+    assert "ACQBULK" in hot and "CCTL.IVALL" in hot and "MEMBAR" in hot
+    assert "RED.E.ADD.64" in hot or "ATOMG.E.ADD.64" in hot
 
 
 def test_struct_layout_matches_c(tmp_path):
