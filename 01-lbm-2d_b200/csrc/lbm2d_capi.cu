@@ -740,8 +740,8 @@ int lbm_run(LbmHandle h, int steps) {
     if (steps < 0) return fail(LBM_ERR_INVALID, "steps < 0");
     const bool strict = h->p.arith == LBM_ARITH_STRICT;
     const int ncols = h->nx_local - 2;
-    // grid of the register variant: x = segment blocks of a column, y (z) = columns followed by the ring rows
-    // `early_cols` > 0: early-start order -- the first columns, then the ring rows, then the other columns --
+    // grid of the register variant: x = segment blocks of a column, y (z) = rows, see step_kernel
+    // `early_cols` > 0: early-start order -- the first column groups, then the W/E ring block, then the other groups --
     // and the rows up to two columns past the ring signal the progress counter (they are what the next
     // step's early columns read and overwrite).  Returns the CTAs that signal per launch in `signals`.
     auto grid_for = [&](lbm::StepArgs &a, int early_cols = 0, unsigned long long *signals = nullptr) {

@@ -212,12 +212,12 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 // "Register" variant.  Interior warps: one warp = one (32 V)-cell segment of one interior column, one
 // thread = V consecutive cells in y; every access is aligned and fully coalesced, the +-1 shift of the
 // pull in y comes from the neighbouring lane by warp shuffle with one extra scalar load at each end of
-// the segment, all issued before first use; no boundary code at all.  Ring warps (blockIdx.y beyond
-// the columns): one ring cell per lane, see above.
+// the segment, all issued before first use; no boundary code at all.  Ring warps (their own grid rows:
+// one row behind every 32 columns for the top / bottom cells, one block of rows for the W / E columns):
+// one ring cell per lane, see above.  BB: optional half-way bounce-back obstacle mode (not the reference's).
 template <bool STRICT, bool EMIT, int V, bool BB = false>
 __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
-    // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows: interior columns, with the
-    // ring rows inserted at ring_row0 (after the early columns; at the end when early start is off)
+    // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows (columns and ring rows, see below)
     const int row = blockIdx.y + blockIdx.z * 65535;
     // Programmatic dependent launch: this grid is scheduled while the previous step drains, and waits here
     // until that grid's writes are complete and visible (a no-op for ordinary launches).  Early start: the
