@@ -320,6 +320,32 @@ def test_early_start_is_bit_identical_to_full_serialisation(pkg, arith, nx, ny, 
         assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and outs[0][2:] == o[2:]
 
 
+@pytest.mark.parametrize("nx,ny", [(2048, 512), (1536, 512), (1280, 768)])
+def test_early_start_long_run_on_grids_of_a_few_waves(pkg, nx, ny, monkeypatch):
+    """The regime where the hand-over is tightest: 2-4 waves of CTAs per step, so the previous step's first columns
+    finish only shortly before its tail and the check goes both ways.  30 000 steps, production arithmetic, stable
+    flow: bit-identical to plain stream-ordered launches."""
+    cfg = make_config(nx, ny, rho_in=1.002, nu=0.05, cs=0.15, warmup=500, sponge=(16, 64, 8, 8))
+    rng = np.random.default_rng(nx)
+    mask = np.zeros((nx, ny), bool)
+    for _ in range(20):
+        w, h = rng.integers(8, 60, 2)
+        x, y = rng.integers(nx // 8, nx // 2), rng.integers(0, ny - h)
+        mask[x:x + w, y:y + h] = True
+    out = []
+    for no_pdl in (False, True):
+        monkeypatch.delenv("LBM2D_NO_PDL", raising=False)
+        if no_pdl:
+            monkeypatch.setenv("LBM2D_NO_PDL", "1")
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask)
+        s.init()
+        for n in (3, 997, 29000):
+            s.run_step(n)
+        out.append(s.f_old.to_numpy())
+        s.close()
+    assert np.isfinite(out[0]).all() and np.array_equal(out[0], out[1])
+
+
 # ------------------------------------------------------------------ long unsteady run: mean fields (north_star: <= 1e-3)
 def test_long_unsteady_run_mean_fields_within_1e3(pkg, tmp_path):
     """30 000 steps of an off-centre cylinder at Re ~ 100 (vortex shedding: the standard deviation of jx over the
