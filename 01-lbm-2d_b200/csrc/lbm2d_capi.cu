@@ -914,7 +914,7 @@ static int get_planes(LbmHandle h, const float *p0, const float *p1, int nch, fl
     if (!out) return fail(LBM_ERR_INVALID, "out is null");
     const size_t n = (size_t)h->p.nx * h->ny * nch;
     if (int rc = ensure_staging(h, n)) return rc;
-    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    dim3 grid(h->p.nx, (h->ny + 127) / 128);
     lbm::pack_planes_kernel<<<grid, 128, 0, h->stream>>>(p0, p1, nch, h->own0, h->ny, h->pitch, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -929,7 +929,7 @@ int lbm_get_mask(LbmHandle h, float *out) {
     if (!out) return fail(LBM_ERR_INVALID, "out is null");
     const size_t n = (size_t)h->p.nx * h->ny;
     if (int rc = ensure_staging(h, n)) return rc;
-    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    dim3 grid(h->p.nx, (h->ny + 127) / 128);
     lbm::mask_to_float_kernel<<<grid, 128, 0, h->stream>>>(h->code, h->own0, h->ny, h->pitch, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -942,7 +942,7 @@ static int export9(LbmHandle h, int mode, float *out) {
     const size_t n = (size_t)h->p.nx * h->ny * 9;
     if (int rc = ensure_staging(h, n)) return rc;
     const lbm::ExportArgs a = make_export_args(h);
-    dim3 grid((h->ny + 127) / 128, h->p.nx);
+    dim3 grid(h->p.nx, (h->ny + 127) / 128);
     lbm::export9_kernel<<<grid, 128, 0, h->stream>>>(a, mode, h->staging);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1086,7 +1086,7 @@ int lbm_export_frame(LbmHandle h, float *out_chw) {
     const bool slabs = h->comm && h->nranks > 1;
     nccl::Api &n = nccl::api();
     if (g.own_cols > 0) {
-        lbm::roi_moments_kernel<<<dim3((g.ch + 127) / 128, g.own_cols), 128, 0, h->stream>>>(a, g, h->exp_tmp);
+        lbm::roi_moments_kernel<<<dim3(g.own_cols, (g.ch + 127) / 128), 128, 0, h->stream>>>(a, g, h->exp_tmp);
         h->launches++;
     }
     if (slabs && (h->exp_send_cols > 0 || h->exp_recv_cols > 0)) {
@@ -1100,7 +1100,7 @@ int lbm_export_frame(LbmHandle h, float *out_chw) {
         NCCL_TRY(n.GroupEnd());
     }
     if (twl > 0) {
-        const dim3 rgrid((g.th + 63) / 64, twl, 9);
+        const dim3 rgrid(twl, (g.th + 63) / 64, 9);
         if (g.fast) lbm::area_fast_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_frame);
         else lbm::area_resize_kernel<<<rgrid, 64, 0, h->stream>>>(h->exp_tmp, g, h->exp_xtab, h->exp_xoff, h->exp_ytab, h->exp_yoff, h->exp_frame);
         h->launches++;

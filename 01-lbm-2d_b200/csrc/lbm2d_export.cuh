@@ -33,8 +33,8 @@ struct ExportGeom {
 
 // 9 moments of the reference's f_new over the ROI -> tmp[c][x][y] (y fastest)
 __global__ void roi_moments_kernel(const ExportArgs a, ExportGeom g, float *__restrict__ tmp) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    const int x = blockIdx.y;   // < own_cols
+    const int y = blockIdx.y * blockDim.x + threadIdx.x;
+    const int x = blockIdx.x;   // < own_cols (grid x: no 65 535 limit on the number of columns)
     if (y >= g.ch) return;
     float f[9], m[9];
     load_f_new(a, g.x0 + x, g.y0 + y, f);
@@ -49,8 +49,8 @@ __global__ void roi_moments_kernel(const ExportArgs a, ExportGeom g, float *__re
 __global__ void area_resize_kernel(const float *__restrict__ tmp, ExportGeom g, const AreaEntry *__restrict__ xtab,
                                    const int *__restrict__ xoff, const AreaEntry *__restrict__ ytab,
                                    const int *__restrict__ yoff, float *__restrict__ out) {
-    const int dy = blockIdx.x * blockDim.x + threadIdx.x;  // lanes along y: neighbouring source rows
-    const int dxl = blockIdx.y, dx = g.dlo + dxl, c = blockIdx.z;
+    const int dy = blockIdx.y * blockDim.x + threadIdx.x;  // lanes along y: neighbouring source rows
+    const int dxl = blockIdx.x, dx = g.dlo + dxl, c = blockIdx.z;
     if (dy >= g.th) return;
     const float *S = tmp + (long long)c * g.cw * g.ch;
     float total = 0.0f;
@@ -68,8 +68,8 @@ __global__ void area_resize_kernel(const float *__restrict__ tmp, ExportGeom g, 
 // resizeAreaFast_: integer scales.  2x2: ((a+b)+(c+d))*0.25 (the SIMD kernel); otherwise the scalar loop
 // unrolled by four the way OpenCV writes it, times 1/area.
 __global__ void area_fast_kernel(const float *__restrict__ tmp, ExportGeom g, float *__restrict__ out) {
-    const int dy = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dxl = blockIdx.y, dx = g.dlo + dxl, c = blockIdx.z;
+    const int dy = blockIdx.y * blockDim.x + threadIdx.x;
+    const int dxl = blockIdx.x, dx = g.dlo + dxl, c = blockIdx.z;
     if (dy >= g.th) return;
     const float *S = tmp + (long long)c * g.cw * g.ch;
     auto at = [&](int sy, int sx) { return S[(long long)(sx - g.src_shift) * g.ch + sy]; };

@@ -451,8 +451,8 @@ __device__ __forceinline__ void load_f_new(const ExportArgs &a, int il, int j, f
 
 // mode 0: moments of f_new (ref:667-737);  1: f_old as AoS;  2: f_new as AoS.   out: (ncols, ny, 9)
 __global__ void export9_kernel(const ExportArgs a, int mode, float *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int il = a.il0 + blockIdx.y;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;   // grid: x = column (no 65 535 limit), y = blocks down the column
+    const int il = a.il0 + blockIdx.x;
     if (j >= a.ny) return;
     float f[9], o9[9];
     if (mode == 1) {
@@ -474,20 +474,20 @@ __global__ void export9_kernel(const ExportArgs a, int mode, float *__restrict__
 
 // (ncols, ny, nch) interleaved from up to 2 pitched planes (vel: ux,uy; rho: one plane).
 __global__ void pack_planes_kernel(const float *p0, const float *p1, int nch, int il0, int ny, int pitch, float *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int il = il0 + blockIdx.y;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    const int il = il0 + blockIdx.x;
     if (j >= ny) return;
     const long long o = (long long)il * pitch + j;
-    float *dst = out + ((long long)blockIdx.y * ny + j) * nch;
+    float *dst = out + ((long long)blockIdx.x * ny + j) * nch;
     dst[0] = p0[o];
     if (nch == 2) dst[1] = p1[o];
 }
 
 __global__ void mask_to_float_kernel(const uint8_t *code, int il0, int ny, int pitch, float *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int il = il0 + blockIdx.y;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    const int il = il0 + blockIdx.x;
     if (j >= ny) return;
-    out[(long long)blockIdx.y * ny + j] = (code[(long long)il * pitch + j] & 1) ? 1.0f : 0.0f;
+    out[(long long)blockIdx.x * ny + j] = (code[(long long)il * pitch + j] & 1) ? 1.0f : 0.0f;
 }
 
 // Momentum exchange over the precomputed solid-fluid links, ref:588-641.

@@ -191,6 +191,22 @@ def test_random_bc_types_and_masks_strict_bit_exact(pkg, kernel):
             assert rel_linf(f.f_old.to_numpy(), ref.f_old) <= TOL, f"trial {trial} fast"
 
 
+def test_very_long_domain_uses_the_z_dimension_of_the_grid(pkg):
+    """nx = 70 000: more than 65 535 grid rows (columns + ring rows), so the row index spills into gridDim.z."""
+    nx, ny = 70000, 40
+    cfg = make_config(nx, ny, rho_in=1.01, nu=0.02, warmup=5, sponge=(16, 64, 4, 4))
+    mask = random_blocks_mask(nx, ny, 400, seed=5, smin=2, smax=12, keep_in=0, keep_out=0)
+    ref = OracleLBMC(cfg, mask)
+    ref.init()
+    ref.run_step(25)
+    for kernel in ("register2", "register"):
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="strict", kernel=kernel)
+        s.init()
+        s.run_step(25)
+        _assert_bit_exact(s, ref, f"{nx}x{ny} {kernel}")
+        s.close()
+
+
 def test_no_mask_and_all_fluid_equivalent(pkg):
     cfg = make_config(48, 24, rho_in=1.01, warmup=5)
     a = pkg.LBM2D_MRT_LES(cfg, mask_data=None, arith="strict")
