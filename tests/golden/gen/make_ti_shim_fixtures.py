@@ -2,7 +2,7 @@
 """Generate tests/golden/ti_shim_*.npz by running the UNMODIFIED reference solver source
 under the pure-Python Taichi stand-in (fake_taichi.py).
 
-Run in the build container (needs /root/reference; ~2-4 minutes):
+Run in the build container (needs /root/reference; ~10 minutes, or name the cases to (re)generate):
     python tests/golden/gen/make_ti_shim_fixtures.py
 
 The tests never read /root/reference -- they read the committed .npz files.
@@ -75,6 +75,20 @@ def mask_b(nx, ny):
     return m
 
 
+def mask_c(nx, ny):
+    """street-canyon style blocks: one flush with the W ring column, one flush with the E ring column, one touching the
+    top ring, one single-cell solid, two blocks one fluid cell apart (a one-cell channel)"""
+    m = np.zeros((nx, ny), bool)
+    m[0:3, 10:15] = True
+    m[nx - 4:nx, 20:26] = True
+    m[12:18, ny - 5:ny] = True
+    m[22, 9] = True
+    m[26:31, 6:14] = True
+    m[26:31, 15:22] = True
+    m[36:40, 1:4] = True
+    return m
+
+
 ZERO4 = [[0.0, 0.0]] * 4
 CASES = {
     # template boundary types, solids touching every wall and two corners
@@ -102,6 +116,16 @@ CASES = {
         cfg=make_config(15, 9, bc_type=[0, 2, 1, 2], bc_value=ZERO4, rho_in=1.015, rho_out=1.0, nu=0.1,
                         cs=0.0005, warmup=0, sponge=(4, 4, 3, 3), strength=1.5, s_ghost=1.0),
         mask=None, snaps=(1, 2, 6, 12, 40)),
+    # larger grid (ny > 32: two pitch lines per column), strong LES, all four sponges, ramp end inside the run
+    "blocks_48x34": dict(
+        cfg=make_config(48, 34, bc_type=[0, 2, 1, 2], bc_value=ZERO4, rho_in=1.03, rho_out=1.0, nu=0.008,
+                        cs=0.17, warmup=30, sponge=(6, 10, 4, 4)),
+        mask=mask_c, snaps=(1, 10, 29, 30, 31, 60, 120)),
+    # long run through and far past the soft-start ramp (frame_count >> warmup_steps), pressure outlet above 1
+    "long_ramp": dict(
+        cfg=make_config(24, 16, bc_type=[0, 2, 1, 2], bc_value=ZERO4, rho_in=1.012, rho_out=1.004, nu=0.015,
+                        cs=0.1, warmup=100, sponge=(3, 6, 2, 2), strength=2.0),
+        mask=mask_a, snaps=(1, 50, 99, 100, 101, 250, 500)),
     # lid-driven cavity: free-slip W/E/bottom, Dirichlet lid on top
     "cavity": dict(
         cfg=make_config(12, 12, bc_type=[2, 0, 2, 2], bc_value=[[0.0, 0.0], [0.06, 0.0], [0.0, 0.0], [0.0, 0.0]],
