@@ -53,6 +53,7 @@ EXPORTS = {
     "lbm_get_rho": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_get_moments": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lbm_get_viz_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lbm_get_f": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "lbm_export_configure": (C.c_int, [C.c_void_p, C.POINTER(LbmExportConfig)]),
     "lbm_export_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

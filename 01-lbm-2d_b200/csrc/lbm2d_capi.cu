@@ -949,6 +949,33 @@ static int export9(LbmHandle h, int mode, float *out) {
     return d2h(h, out, h->staging, n * sizeof(float));
 }
 
+int lbm_get_viz_fields(LbmHandle h, const double *weights, int radius, float *out_mag, float *out_vor) {
+    if (int rc = check_handle(h, true)) return rc;
+    if (!out_mag || !out_vor) return fail(LBM_ERR_INVALID, "out is null");
+    if (radius < 0 || radius > 4096 || (radius > 0 && !weights)) return fail(LBM_ERR_INVALID, "bad filter radius / weights");
+    if (!(h->west_ring && h->east_ring)) return fail(LBM_ERR_INVALID, "viz fields: single GPU only (the filter reaches across slab borders)");
+    const int nx = h->p.nx, ny = h->ny;
+    const size_t n = (size_t)nx * ny, wfloats = 2 * ((size_t)radius + 2);   // the weights ride in front (8-byte aligned)
+    if (int rc = ensure_staging(h, wfloats + 6 * n)) return rc;
+    double *w = reinterpret_cast<double *>(h->staging);
+    float *t0 = h->staging + wfloats, *t1 = t0 + n, *v0 = t1 + n, *v1 = v0 + n, *mag = v1 + n, *vor = mag + n;
+    const dim3 grid(nx, (ny + 127) / 128);
+    const float *vx = h->ux, *vy = h->uy;
+    long long sx = h->pitch;
+    if (radius > 0) {
+        CUDA_TRY(cudaMemcpyAsync(w, weights, ((size_t)radius + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        lbm::viz_blur_kernel<<<grid, 128, 0, h->stream>>>(h->ux, h->uy, h->pitch, nx, ny, 0, radius, w, t0, t1);
+        lbm::viz_blur_kernel<<<grid, 128, 0, h->stream>>>(t0, t1, ny, nx, ny, 1, radius, w, v0, v1);
+        vx = v0; vy = v1; sx = ny;
+        h->launches += 2;
+    }
+    lbm::viz_fields_kernel<<<grid, 128, 0, h->stream>>>(vx, vy, sx, nx, ny, mag, vor);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (int rc = d2h(h, out_mag, mag, n * sizeof(float))) return rc;
+    return d2h(h, out_vor, vor, n * sizeof(float));
+}
+
 int lbm_get_moments(LbmHandle h, float *out) { return export9(h, 0, out); }
 int lbm_get_f(LbmHandle h, int which, float *out) {
     if (which != 0 && which != 1) return fail(LBM_ERR_INVALID, "which must be 0 (f_old) or 1 (f_new)");

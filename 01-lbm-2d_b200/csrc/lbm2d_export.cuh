@@ -177,4 +177,56 @@ __global__ void export_minmax_kernel(const float *__restrict__ frame, long long 
     }
 }
 
+// ---- video-frame fields (Taichi_Gui_Viz.process_frame, viz:22-34) ---------------------------------------------
+// mode="reflect" of scipy.ndimage: (d c b a | a b c d | d c b a), any distance past the edge
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - 1 - i;
+}
+
+// One pass of NI_Correlate1D (symmetric kernel): centre tap first, then the pairs from the outermost inwards,
+// (in[-j] + in[+j]) * w[j], accumulated in double with every operation rounded on its own; float32 out.
+// in: element (x, y) at x * sx + y; out: (nx, ny) unpitched.  axis 0 = along x, 1 = along y.  Two fields at once.
+__global__ void viz_blur_kernel(const float *__restrict__ in0, const float *__restrict__ in1, long long sx, int nx, int ny,
+                                int axis, int radius, const double *__restrict__ w, float *__restrict__ out0,
+                                float *__restrict__ out1) {
+    const int y = blockIdx.y * blockDim.x + threadIdx.x, x = blockIdx.x;
+    if (y >= ny) return;
+    const int pos = axis == 0 ? x : y, n = axis == 0 ? nx : ny;
+    auto at = [&](const float *in, int q) {
+        return (double)(axis == 0 ? in[(long long)q * sx + y] : in[(long long)x * sx + q]);
+    };
+    double a0 = __dmul_rn(at(in0, pos), w[0]), a1 = __dmul_rn(at(in1, pos), w[0]);
+    for (int j = radius; j > 0; --j) {
+        const int lo = reflect_index(pos - j, n), hi = reflect_index(pos + j, n);
+        a0 = __dadd_rn(a0, __dmul_rn(__dadd_rn(at(in0, lo), at(in0, hi)), w[j]));
+        a1 = __dadd_rn(a1, __dmul_rn(__dadd_rn(at(in1, lo), at(in1, hi)), w[j]));
+    }
+    const long long o = (long long)x * ny + y;
+    out0[o] = __double2float_rn(a0);
+    out1[o] = __double2float_rn(a1);
+}
+
+// vel_mag = sqrt(vx^2 + vy^2); vor = np.gradient(vx)[1] - np.gradient(vy)[0] (float32: central differences / 2 inside,
+// one-sided at the edges).  vx, vy: element (x, y) at x * sx + y.
+__global__ void viz_fields_kernel(const float *__restrict__ vx, const float *__restrict__ vy, long long sx, int nx, int ny,
+                                  float *__restrict__ mag, float *__restrict__ vor) {
+    const int y = blockIdx.y * blockDim.x + threadIdx.x, x = blockIdx.x;
+    if (y >= ny) return;
+    auto U = [&](int xx, int yy) { return vx[(long long)xx * sx + yy]; };
+    auto Vv = [&](int xx, int yy) { return vy[(long long)xx * sx + yy]; };
+    const float u = U(x, y), v = Vv(x, y);
+    const float dudy = (y == 0)        ? __fsub_rn(U(x, 1), U(x, 0))
+                       : (y == ny - 1) ? __fsub_rn(U(x, ny - 1), U(x, ny - 2))
+                                       : __fdiv_rn(__fsub_rn(U(x, y + 1), U(x, y - 1)), 2.0f);
+    const float dvdx = (x == 0)        ? __fsub_rn(Vv(1, y), Vv(0, y))
+                       : (x == nx - 1) ? __fsub_rn(Vv(nx - 1, y), Vv(nx - 2, y))
+                                       : __fdiv_rn(__fsub_rn(Vv(x + 1, y), Vv(x - 1, y)), 2.0f);
+    const long long o = (long long)x * ny + y;
+    mag[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+    vor[o] = __fsub_rn(dudy, dvdx);
+}
+
 }  // namespace lbm

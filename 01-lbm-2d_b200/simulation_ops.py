@@ -91,8 +91,11 @@ def run_simulation_loop(config, solver, viz, recorder, gui, writer, max_steps, p
             vid_frame = out_cfg["video"]["enable"] and done % vid_every == 0 and done >= start_record
             img = None
             if (gui_frame or vid_frame) and viz is not None:
-                vel, mask = solver.get_physical_fields()
-                img = viz.process_frame(vel, mask)
+                if hasattr(viz, "process_frame_from_solver"):   # device-side fields (gui_viz.DeviceGuiViz)
+                    img = viz.process_frame_from_solver(solver)
+                else:
+                    vel, mask = solver.get_physical_fields()
+                    img = viz.process_frame(vel, mask)
             if gui_frame and gui and img is not None:
                 gui.set_image(img)
                 gui.show()

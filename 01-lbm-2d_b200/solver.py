@@ -183,6 +183,25 @@ class LBM2D_MRT_LES:
                 "running_count": int(cnt.value)}
 
     # ------------------------------------------------------------------ extras
+    def get_viz_fields(self, sigma=None):
+        """(vel_mag, vorticity), (nx, ny) float32 each: the numeric part of the reference's video frame
+        (`visualization/Taichi_Gui_Viz.py:22-34` -- scipy gaussian_filter of both velocity components, |u|,
+        np.gradient vorticity) computed on the device, bit-identical to scipy / numpy on `vel.to_numpy()`.
+        `sigma` defaults to the config's `outputs.gui.gaussian_sigma`; <= 0 switches the filter off."""
+        sigma = float(self.viz_sigma if sigma is None else sigma)
+        radius, wptr = 0, None
+        if sigma > 0:   # scipy/ndimage/_filters.py: _gaussian_kernel1d with truncate = 4.0
+            radius = int(4.0 * sigma + 0.5)
+            x = np.arange(-radius, radius + 1)
+            phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+            weights = np.ascontiguousarray((phi / phi.sum())[radius:], dtype=np.float64)
+            wptr = weights.ctypes.data_as(C.c_void_p)
+        mag = np.empty((self._nx_owned, self.ny), np.float32)
+        vor = np.empty((self._nx_owned, self.ny), np.float32)
+        _capi.check(self._lib.lbm_get_viz_fields(self._h, wptr, radius, mag.ctypes.data_as(C.c_void_p),
+                                                 vor.ctypes.data_as(C.c_void_p)))
+        return mag, vor
+
     def step_count(self) -> int:
         v = C.c_int64()
         _capi.check(self._lib.lbm_step_count(self._h, C.byref(v)))

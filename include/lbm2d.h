@@ -124,6 +124,14 @@ int lbm_get_mask(LbmHandle h, float *out_nxny);
  * channel order [rho, e, eps, jx, qx, jy, qy, pxx, pxy], taken from the reference's f_new:
  * post-collision values at interior cells (solids included), the initial equilibrium on the ring. */
 int lbm_get_moments(LbmHandle h, float *out_nxny9);
+/* The numeric part of the reference's video frame, Taichi_Gui_Viz.process_frame
+ * (src/lbm_mrt_les/visualization/Taichi_Gui_Viz.py:22-34), computed on the device instead of on the host from
+ * get_physical_fields(): scipy.ndimage.gaussian_filter of both velocity components (restated operation for
+ * operation: separable, axis 0 then 1, double accumulation, mode "reflect", float32 between the passes),
+ * |u| and the np.gradient vorticity.  weights[0..radius] = the taps of scipy's kernel at distance 0..radius
+ * (float64, computed by the caller the way scipy does); radius = 0 / weights = NULL = no filter (viz_sigma <= 0).
+ * out_mag, out_vor: (nx, ny) float32 each.  Single GPU (the filter reaches across slab borders). */
+int lbm_get_viz_fields(LbmHandle h, const double *weights, int radius, float *out_mag_nxny, float *out_vor_nxny);
 /* f_old.to_numpy() (which = 0) / f_new.to_numpy() (which = 1): (nx,ny,9).  Parity / debugging. */
 int lbm_get_f(LbmHandle h, int which, float *out_nxny9);
 

@@ -3,6 +3,7 @@ stand-in solver.  Mirrors reference behaviour documented in SURVEY.md 3.3 (core/
 import importlib
 
 import numpy as np
+import pytest
 
 from helpers import make_config
 
@@ -82,3 +83,46 @@ def test_loop_reports_exceptions_as_error_status():
 
     meta = ops.run_simulation_loop(_cfg(), Boom(lambda n: 0.0), None, None, None, None, max_steps=10, progress=False)
     assert meta["status"] == "Error" and "device lost" in meta["reason"] and meta["final_steps"] == 0
+
+
+def test_video_frames_take_the_device_fields_when_the_viz_offers_them():
+    """`DeviceGuiViz` (process_frame_from_solver) is asked instead of get_physical_fields + process_frame; a plain viz
+    object keeps the reference's call sequence (ops:146-152)."""
+    import importlib
+
+    gv = importlib.import_module("01-lbm-2d_b200.gui_viz")
+
+    class S(ScriptedSolver):
+        def get_viz_fields(self, sigma):
+            self.calls.append(("viz_fields", sigma))
+            return np.full((self.nx, self.ny), 0.1, np.float32), np.zeros((self.nx, self.ny), np.float32)
+
+        def get_physical_fields(self):
+            self.calls.append(("fields", self.steps))
+            return np.zeros((self.nx, self.ny, 2), np.float32), np.zeros((self.nx, self.ny), np.float32)
+
+    class Rec:
+        frames = []
+
+        def write_frame(self, f):
+            self.frames.append(f.shape)
+
+    class HostViz:
+        def process_frame(self, vel, mask):
+            return np.zeros((8, 8, 3), np.float32)
+
+    cfg = _cfg()
+    cfg["outputs"]["video"]["enable"] = True
+    cfg["outputs"]["video"]["interval_steps"] = 20
+    s, rec = S(lambda n: 0.1), Rec()
+    colour = lambda f, mask=None, **kw: np.repeat(f[..., None], 3, axis=2)  # noqa: E731
+    viz = gv.DeviceGuiViz(16, 4, viz_sigma=1.5, colorize_velocity=colour, colorize_vorticity=colour)
+    s.mask = type("M", (), {"to_numpy": staticmethod(lambda: np.zeros((8, 4), np.float32))})()
+    ops.run_simulation_loop(cfg, s, viz, rec, None, None, max_steps=60, progress=False)
+    assert [c for c in s.calls if c[0] == "viz_fields"] == [("viz_fields", 1.5)] * 2      # steps 40, 60 (>= start_record 30)
+    assert not [c for c in s.calls if c[0] == "fields"] and rec.frames == [(8, 8, 3)] * 2   # (nx, 2 ny, 3) = (8, 8, 3), transposed
+    s2 = S(lambda n: 0.1)
+    ops.run_simulation_loop(cfg, s2, HostViz(), Rec(), None, None, max_steps=60, progress=False)
+    assert len([c for c in s2.calls if c[0] == "fields"]) == 2 and not [c for c in s2.calls if c[0] == "viz_fields"]
+    with pytest.raises(TypeError):
+        viz.process_frame(None, None)
