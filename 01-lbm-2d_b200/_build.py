@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblbm2d.so")
 SOURCES = ["lbm2d_capi.cu"]
-HEADERS = ["lbm2d_device.cuh", "lbm2d_kernels.cuh", "lbm2d_tma.cuh", "lbm2d_export.cuh", "lbm2d_async.cuh", os.path.join("..", "..", "include", "lbm2d.h")]
+HEADERS = ["lbm2d_device.cuh", "lbm2d_kernels.cuh", "lbm2d_tma.cuh", "lbm2d_export.cuh", os.path.join("..", "..", "include", "lbm2d.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

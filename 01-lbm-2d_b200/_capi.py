@@ -34,9 +34,10 @@ class LbmDeviceView(C.Structure):
     ]
 
 
+ABI_VERSION = 2  # LBM2D_ABI_VERSION of include/lbm2d.h
 COMM_ID_BYTES = 128
 ARITH = {"fast": 0, "strict": 1}
-KERNEL = {"auto": 0, "register": 1, "tma": 2, "register2": 3, "register1": 4, "async": 5}
+KERNEL = {"auto": 0, "register": 1, "tma": 2}
 EXPORTS = {
     "lbm_abi_version": (C.c_int, []),
     "lbm_last_error": (C.c_char_p, []),
@@ -63,6 +64,7 @@ EXPORTS = {
     "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),
     "lbm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "lbm_selftest_arith": (C.c_int, [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -87,7 +89,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.lbm_abi_version() != 1:
+    if lib.lbm_abi_version() != ABI_VERSION:
         raise LbmError("liblbm2d.so ABI version mismatch")
     _lib = lib
     return lib

@@ -15,7 +15,6 @@
 #include <thread>
 #include <vector>
 
-#include "lbm2d_async.cuh"
 #include "lbm2d_export.cuh"
 #include "lbm2d_tma.cuh"
 
@@ -96,19 +95,17 @@ struct LbmSolver {
     uint8_t *links8 = nullptr;            // bounce-back mode only
     float *damp_x = nullptr, *damp_y = nullptr, *ramp_tab = nullptr;
     int *ctr = nullptr;
+    std::vector<float> ramp_host;          // ramp_at(t), t = 0 .. warmup_steps (ref:442-443)
     float *mac = nullptr;  // rho | ux | uy, three consecutive planes (one TMA store tensor)
     float *rho = nullptr, *ux = nullptr, *uy = nullptr;
     unsigned *maxv = nullptr;
     lbm::RingCtx *ring_ctx = nullptr;  // [2], one per destination buffer
     bool use_tma = false;
-    int vwidth = 4;  // cells per thread of the register variant
-    bool use_async = false;
     bool use_pdl = true;
     long long early_min_ctas = 2500;      // grids with fewer CTAs keep the plain PDL hand-over
     int early_target = 1500;              // CTAs that may start on the progress counter (0 = early start off)
     unsigned long long *progress = nullptr;   // device counter, see step_kernel
     unsigned long long progress_total = 0;    // its value once every step launched so far has signalled
-    int async_grid = 0;
     int tma_grid = 0;
     CUtensorMap map_src[2], map_srch[2], map_dst[2], map_code, map_mac;
     lbm::TmaArgs tma_args{};
@@ -244,16 +241,21 @@ float ramp_at(int t, int warmup) {
 lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     lbm::StepArgs a{};
     const int par = par_override >= 0 ? par_override : (int)(s->steps_done & 1);
+    static const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
     a.src = s->f[par];
     a.dst = s->f[par ^ 1];
+    for (int k = 0; k < 9; ++k) {
+        a.srcp[k] = a.src + k * s->plane - (long long)ex[k] * s->pitch;
+        a.dstp[k] = a.dst + k * s->plane;
+    }
     a.code = s->code;
     a.code_bits = s->code_bits;
     a.links8 = s->links8;
     a.damp_x = s->damp_x;
     a.damp_y = s->damp_y;
-    a.ramp_tab = s->ramp_tab;
-    a.ctr_in = s->ctr + par;
     a.ctr_out = s->ctr + (par ^ 1);
+    a.frame = (int)(s->steps_done + 1);
+    a.ramp = s->ramp_host[std::min<int64_t>(s->steps_done + 1, s->p.warmup_steps)];
     a.rho = s->rho;
     a.ux = s->ux;
     a.uy = s->uy;
@@ -266,7 +268,6 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.x_off = s->x_off;
     a.west_ring = s->west_ring;
     a.east_ring = s->east_ring;
-    a.warmup = s->p.warmup_steps;
     a.ring = s->ring_ctx + (par ^ 1);
     a.il0 = 1;
     a.il_step = 1;
@@ -417,11 +418,8 @@ int exchange_halos(LbmSolver *s, float *buf, cudaStream_t st) {
 }
 
 typedef void (*StepFn)(const lbm::StepArgs);
-StepFn step_fn(bool strict, bool emit, int v, bool bb = false) {
-    if (bb)   // bounce-back obstacle mode: 2 cells per thread only
-        return strict ? (emit ? (StepFn)lbm::step_kernel<true, true, 2, true> : (StepFn)lbm::step_kernel<true, false, 2, true>)
-                      : (emit ? (StepFn)lbm::step_kernel<false, true, 2, true> : (StepFn)lbm::step_kernel<false, false, 2, true>);
-#define LBM_PICK(S, E) (v == 4 ? (StepFn)lbm::step_kernel<S, E, 4> : v == 2 ? (StepFn)lbm::step_kernel<S, E, 2> : (StepFn)lbm::step_kernel<S, E, 1>)
+StepFn step_fn(bool strict, bool emit, bool bb = false) {
+#define LBM_PICK(S, E) (bb ? (StepFn)lbm::step_kernel<S, E, true> : (StepFn)lbm::step_kernel<S, E, false>)
     return strict ? (emit ? LBM_PICK(true, true) : LBM_PICK(true, false)) : (emit ? LBM_PICK(false, true) : LBM_PICK(false, false));
 #undef LBM_PICK
 }
@@ -473,7 +471,7 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     if (p.obstacle_mode != LBM_OBSTACLE_REFILL && p.obstacle_mode != LBM_OBSTACLE_BOUNCE_BACK)
         return fail(LBM_ERR_INVALID, "unsupported obstacle_mode");
     if (p.obstacle_mode == LBM_OBSTACLE_BOUNCE_BACK &&
-        ((p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER2) || (p.nx_global > 0 && p.nx_global != p.nx)))
+        ((p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER) || (p.nx_global > 0 && p.nx_global != p.nx)))
         return fail(LBM_ERR_INVALID, "obstacle_mode bounce-back: single GPU and the default kernel only");
     if (p.arith != LBM_ARITH_FAST && p.arith != LBM_ARITH_STRICT) return fail(LBM_ERR_INVALID, "unsupported arith");
     if (p.warmup_steps > (1 << 26)) return fail(LBM_ERR_INVALID, "warmup_steps too large for the ramp table");
@@ -502,11 +500,9 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         return fail(LBM_ERR_INVALID, "a slab needs at least 3 local columns");
     }
     s->ny = p.ny;
-    s->pitch = round_up(p.ny, 32);
+    s->pitch = round_up(p.ny, lbm::kSegCells);   // every lane of every segment warp stays inside its column
     s->plane = (long long)s->nx_local * s->pitch;
-    // AUTO -> the 2-cells-per-thread register variant (fastest measured: profiles/)
-    s->vwidth = (p.kernel == LBM_KERNEL_REGISTER) ? 4 : (p.kernel == LBM_KERNEL_REGISTER1 ? 1 : 2);
-    s->nseg = (s->pitch + 32 * s->vwidth - 1) / (32 * s->vwidth);
+    s->nseg = s->pitch / lbm::kSegCells;
     s->n_items = (s->nx_local - 2) * s->nseg;
 
     // fp32 constants, derived like the reference's Python scope + Taichi f32 casts
@@ -524,6 +520,13 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         s->phys.bc_val[d][1] = p.bc_value[d][1];
     }
     s->phys.nx_global = p.nx_global;
+    {   // where the packed division / square-root sequences of the strict collision need no range checks (Lane2)
+        auto in = [](double v, double lo, double hi) { return v >= lo && v <= hi; };
+        const double strength = (float)p.sponge_strength;
+        s->phys.fast_div_ok = in(s->phys.tau0, 0x1p-10, 0x1p20) && in(s->phys.tau0_sq, 0x1p-20, 0x1p40) &&
+                              (!s->phys.les_on || in(s->phys.cs_factor, 0x1p-20, 0x1p20)) && in(strength, 0.0, 0x1p30) &&
+                              !std::getenv("LBM2D_NO_FAST_DIV");
+    }
 
 #define CREATE_TRY(expr)                                                                            \
     do {                                                                                            \
@@ -595,7 +598,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     CREATE_TRY(cudaMemcpy(s->damp_x, dx.data(), dx.size() * sizeof(float), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(s->damp_y, dy.data(), dy.size() * sizeof(float), cudaMemcpyHostToDevice));
 
-    std::vector<float> ramp((size_t)p.warmup_steps + 1);
+    std::vector<float> &ramp = s->ramp_host;
+    ramp.resize((size_t)p.warmup_steps + 1);
     for (int t = 0; t <= p.warmup_steps; ++t) ramp[t] = ramp_at(t, p.warmup_steps);
     CREATE_TRY(cudaMemcpy(s->ramp_tab, ramp.data(), ramp.size() * sizeof(float), cudaMemcpyHostToDevice));
 
@@ -655,21 +659,10 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         (void)tiles;
         s->use_tma = p.kernel == LBM_KERNEL_TMA;
-        s->use_async = p.kernel == LBM_KERNEL_ASYNC;
         s->use_pdl = !std::getenv("LBM2D_NO_PDL");
         if (const char *e = std::getenv("LBM2D_EARLY_CTAS")) s->early_target = std::max(0, std::atoi(e));
         if (const char *e = std::getenv("LBM2D_EARLY_MIN_CTAS")) s->early_min_ctas = std::max(0, std::atoi(e));
-        if (s->use_async) {
-            const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
-            int per_sm = 0;
-            for (auto fnp : {(const void *)lbm::step_async_kernel<false, false>, (const void *)lbm::step_async_kernel<false, true>,
-                             (const void *)lbm::step_async_kernel<true, false>, (const void *)lbm::step_async_kernel<true, true>})
-                cudaFuncSetAttribute(fnp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::step_async_kernel<false, false>, 32 * lbm::kAWarps, smem);
-            if (std::getenv("LBM2D_ASYNC_CTAS")) per_sm = std::min(per_sm, std::atoi(std::getenv("LBM2D_ASYNC_CTAS")));
-            s->async_grid = std::max(1, per_sm) * sms;
-        }
-        if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_ASYNC) {
+        if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_TMA) {
             delete s;
             return fail(LBM_ERR_INVALID, "unsupported kernel variant");
         }
@@ -742,8 +735,9 @@ int lbm_run(LbmHandle h, int steps) {
     const int ncols = h->nx_local - 2;
     // grid of the register variant: x = segment blocks of a column, y (z) = rows, see step_kernel
     // `early_cols` > 0: early-start order -- the first column groups, then the W/E ring block, then the other groups --
-    // and the rows up to two columns past the ring signal the progress counter (they are what the next
-    // step's early columns read and overwrite).  Returns the CTAs that signal per launch in `signals`.
+    // and the rows up to one whole group (its top / bottom ring row included) past the ring signal the progress
+    // counter: they are what the next step's early columns read (columns c-1..c+1, the ring cells of column
+    // early_cols + 1 included) and overwrite (source columns whose last readers are that group's ring warps).  Returns the CTAs that signal per launch in `signals`.
     auto grid_for = [&](lbm::StepArgs &a, int early_cols = 0, unsigned long long *signals = nullptr) {
         const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
         const int G = lbm::kRingGroup;
@@ -755,7 +749,7 @@ int lbm_run(LbmHandle h, int steps) {
         a.ring_rows = (we_ctas + gx - 1) / gx;
         a.ring_row0 = early_cols > 0 ? early_cols / G * (G + 1) : vrows;
         a.early_rows = 0;
-        a.low_rows = early_cols > 0 ? a.ring_row0 + a.ring_rows + 2 : 0;
+        a.low_rows = early_cols > 0 ? a.ring_row0 + a.ring_rows + (G + 1) : 0;
         if (signals) *signals = (unsigned long long)a.low_rows * gx;
         const int rows = vrows + a.ring_rows;
         return dim3(gx, std::min(rows, 65535), (rows + 65534) / 65535);
@@ -770,7 +764,7 @@ int lbm_run(LbmHandle h, int steps) {
         // below ~2 waves of CTAs the previous step's first columns are not done when its last CTAs start: the
         // check would always fall through to the wait and the counter update would only lengthen the step
         const long long total_ctas = (long long)ncols * gx;
-        if (h->use_pdl && single && !h->use_tma && !h->use_async && want >= 4 && total_ctas >= h->early_min_ctas) early_cols = want;
+        if (h->use_pdl && single && !h->use_tma && want >= 4 && total_ctas >= h->early_min_ctas) early_cols = want;
     }
     lbm::StepArgs a_all = make_args(h);
     unsigned long long signals_all = 0;
@@ -817,17 +811,7 @@ int lbm_run(LbmHandle h, int steps) {
             if (emit) CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));  // orders the max|u| reset before the edge kernel
             CUDA_TRY(cudaStreamWaitEvent(h->stream_e, h->ev_m, 0));
             const dim3 eb = grid_for(e);
-#define LBM_LAUNCH_EDGE(S, E, V) lbm::step_kernel<S, E, V><<<eb, lbm::kThreads, 0, h->stream_e>>>(e)
-#define LBM_LAUNCH_EV(V)                                                     \
-    do {                                                                    \
-        if (strict) { if (emit) LBM_LAUNCH_EDGE(true, true, V); else LBM_LAUNCH_EDGE(true, false, V); } \
-        else { if (emit) LBM_LAUNCH_EDGE(false, true, V); else LBM_LAUNCH_EDGE(false, false, V); }      \
-    } while (0)
-            if (h->vwidth == 4) LBM_LAUNCH_EV(4);
-            else if (h->vwidth == 2) LBM_LAUNCH_EV(2);
-            else LBM_LAUNCH_EV(1);
-#undef LBM_LAUNCH_EV
-#undef LBM_LAUNCH_EDGE
+            CUDA_TRY(launch_step(step_fn(strict, emit, false), eb, h->stream_e, e, false));
             CUDA_TRY(cudaEventRecord(h->ev_e, h->stream_e));
             if (int rc = exchange_halos(h, a.dst, h->stream_e)) return rc;
             h->launches++;
@@ -835,19 +819,13 @@ int lbm_run(LbmHandle h, int steps) {
             blocks = grid_for(a);
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_e_prev_valid ? h->ev_e_prev : h->ev_e, 0));
         }
-        if (h->use_async) {
-            const int smem = lbm::kAWarps * lbm::kAStages * lbm::kAStageFloats * 4;
-            const int nseg64 = (h->pitch + lbm::kASeg - 1) / lbm::kASeg;
-            const int grid = std::min(h->async_grid, (a.il_count * nseg64 + lbm::kAWarps - 1) / lbm::kAWarps);
-            if (strict) { if (emit) lbm::step_async_kernel<true, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<true, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
-            else { if (emit) lbm::step_async_kernel<false, true><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); else lbm::step_async_kernel<false, false><<<grid, 32 * lbm::kAWarps, smem, st>>>(a); }
-        } else {
+        {
             // PDL between consecutive plain steps of a batch (not across the max|u| memset of an EMIT step)
             const bool pdl = h->use_pdl && !overlap && !emit && it > 0;
             // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
             a.early_rows = (pdl && early_cols > 0) ? a_all.ring_row0 : 0;
             a.progress_expected = h->progress_total;
-            CUDA_TRY(launch_step(step_fn(strict, emit, h->vwidth, h->links8 != nullptr), blocks, st, a, pdl));
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr), blocks, st, a, pdl));
             if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;
@@ -1195,6 +1173,22 @@ int lbm_device_view(LbmHandle h, LbmDeviceView *out) {
     out->pitch = h->pitch;
     out->plane_stride = h->plane;
     out->stream = (void *)h->stream;
+    return LBM_OK;
+}
+
+int lbm_selftest_arith(int64_t pairs, uint64_t seed, int64_t mismatches[3]) {
+    if (!mismatches || pairs < 0) return fail(LBM_ERR_INVALID, "bad argument");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+    const int blocks = 1184, threads = 256;
+    const long long per = (pairs + (long long)blocks * threads - 1) / ((long long)blocks * threads);
+    lbm::selftest_arith_kernel<<<blocks, threads>>>(per, seed, d);
+    unsigned long long h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+    for (int k = 0; k < 3; ++k) mismatches[k] = (int64_t)h[k];
     return LBM_OK;
 }
 

@@ -1,10 +1,9 @@
 // Kernels of the fused D2Q9 MRT-LES step (sm_100a).  See DESIGN.md for the data layout.
 //
 // Layout in HBM: 9 SoA planes per buffer, each (nx_local, pitch) with y fastest and
-// pitch = round_up(ny, 32) floats, so every column starts on a 128-byte line and a warp's
+// pitch = round_up(ny, 64) floats, so every column starts on a 128-byte line and a warp's
 // vector accesses are full, aligned lines.  Two buffers (src/dst) swap roles every step.
-// Variants: step_kernel (register, default; this file), step_tma_kernel (lbm2d_tma.cuh),
-// step_async_kernel (lbm2d_async.cuh).
+// Variants: step_kernel (register, default; this file), step_tma_kernel (lbm2d_tma.cuh).
 #pragma once
 #include "lbm2d_device.cuh"
 
@@ -12,42 +11,42 @@ namespace lbm {
 
 // Tuning knobs (measured on B200, 8192x2048: profiles/r01_tuning_sweep.md).  Small CTAs (64-128 threads) win:
 // the warps of a CTA move through load / math / store in lock-step, so many small CTAs per SM keep the
-// memory pipeline evenly fed.
+// memory pipeline evenly fed.  Two cells per thread (64-bit accesses) beat one and four (same file).
 #ifndef LBM_WPB
 #define LBM_WPB 4
 #endif
-#ifndef LBM_MINB2
-#define LBM_MINB2 10
-#endif
-#ifndef LBM_MINB1
-#define LBM_MINB1 12
-#endif
-#ifndef LBM_STCS
-#define LBM_STCS 0
+#ifndef LBM_MINB
+#define LBM_MINB 10
 #endif
 constexpr int kWarpsPerBlock = LBM_WPB;
 static_assert(LBM_WPB >= 2, "the top / bottom ring row of a group needs two warps");
 constexpr int kRingGroup = 32;   // interior columns per top/bottom ring row of the grid (one lane per column)
 constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kCellsPerThread = 2;                       // one 64-bit access per plane, one packed fp32 pair per value
+constexpr int kSegCells = 32 * kCellsPerThread;          // cells per warp; the plane pitch is a multiple of this
 
 struct StepArgs {
     const float *__restrict__ src;  // 9 planes
     float *__restrict__ dst;        // 9 planes
+    // plane k of the source buffer shifted by the pull: srcp[k] + il * pitch + j is f_k(il - e_kx, j), and plane k of
+    // the destination.  Kernel parameters live in the constant bank, so an access is ONE instruction (32-bit cell
+    // offset * 4 + 64-bit constant) instead of a 64-bit multiply-add chain per plane.
+    const float *srcp[9];
+    float *dstp[9];
     const uint8_t *__restrict__ code;  // cell code, bit0 = solid
     const uint8_t *__restrict__ links8;  // bounce-back mode only: bit k-1 set = the upstream neighbour i - e_k of this FLUID cell is solid
     const uint32_t *__restrict__ code_bits;  // the same bit, 32 cells per word (plane order): what the interior warps read
     const float *__restrict__ damp_x;  // [nx_local]   ref:364-370 (indexed by local column, holds the global value)
     const float *__restrict__ damp_y;  // [pitch]      ref:372-378
-    const float *__restrict__ ramp_tab;  // [warmup+1]  ref:442-443
-    const int *ctr_in;              // frame_count before this step
-    int *ctr_out;                   // frame_count after this step (other parity slot)
+    int *ctr_out;                   // device copy of frame_count (diagnostic; the kernels use `frame` / `ramp`)
     float *rho, *ux, *uy;           // macroscopic planes (written by EMIT steps)
     unsigned *maxv_bits;            // max(ux^2+uy^2) as ordered uint; [1] = NaN flag
     long long plane;                // floats per plane = nx_local * pitch
     int nx_local, ny, pitch, nseg;
     int x_off;                      // global x of local column 0
     int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
-    int warmup;
+    int frame;                      // frame_count after this step (ref:440), known on the host
+    float ramp;                     // soft-start factor of this step, ref:442-443 (host table, see lbm2d_capi.cu)
     int il0, il_step, il_count;     // columns of this launch: il0 + blockIdx.y * il_step, blockIdx.y < il_count
     int bump_ctr;                   // this launch advances frame_count (exactly one launch per step does)
     int n_ring;                     // ring cells handled by this launch's ring warps
@@ -57,7 +56,7 @@ struct StepArgs {
     int early_rows, low_rows;
     unsigned long long *progress;
     unsigned long long progress_expected;   // counter value once the previous step's rows [0, low_rows) are complete
-    const RingCtx *ring;            // rare-path context in global memory (dst-specific)
+    const RingCtx *ring;            // rare-path context in global memory (dst-specific; TMA variant)
     Physics phys;
 };
 
@@ -65,48 +64,8 @@ __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
     return __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy));
 }
 
-// aligned V-wide global accesses (V = 1, 2, 4 floats)
 // Population loads bypass L1 (ld.global.cg): every value is read exactly once per step; measured 1 % faster.
-#ifndef LBM_LDCS
-#define LBM_LDCS 2
-#endif
-#if LBM_LDCS == 2
 #define LBM_LD(ptr) __ldcg(ptr)
-#elif LBM_LDCS
-#define LBM_LD(ptr) __ldcs(ptr)
-#else
-#define LBM_LD(ptr) __ldg(ptr)
-#endif
-template <int V>
-__device__ __forceinline__ void ldf(const float *p, float (&o)[V]) {   // populations: read exactly once per step
-    if (V == 4) { const float4 t = LBM_LD(reinterpret_cast<const float4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
-    else if (V == 2) { const float2 t = LBM_LD(reinterpret_cast<const float2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
-    else o[0] = LBM_LD(p);
-}
-template <int V>
-__device__ __forceinline__ void ldv(const float *p, float (&o)[V]) {
-    if (V == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
-    else if (V == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
-    else o[0] = __ldg(p);
-}
-template <int V>
-__device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
-#if LBM_STCS
-    if (V == 4) __stcs(reinterpret_cast<float4 *>(p), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
-    else if (V == 2) __stcs(reinterpret_cast<float2 *>(p), make_float2(o[0], o[1 % V]));
-    else __stcs(p, o[0]);
-#else
-    if (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
-    else if (V == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1 % V]);
-    else *p = o[0];
-#endif
-}
-template <int V>
-__device__ __forceinline__ void ldcode(const uint8_t *p, unsigned char (&o)[V]) {
-    if (V == 4) { const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(p)); o[0] = t.x; o[1 % V] = t.y; o[2 % V] = t.z; o[3 % V] = t.w; }
-    else if (V == 2) { const uchar2 t = __ldg(reinterpret_cast<const uchar2 *>(p)); o[0] = t.x; o[1 % V] = t.y; }
-    else o[0] = __ldg(p);
-}
 
 // Half-way bounce-back (optional obstacle mode, not the reference's): a population whose upstream neighbour is
 // solid is replaced by the cell's own post-collision population of the opposite direction from the
@@ -140,7 +99,7 @@ __host__ __device__ inline int ring_cell_count(int il0, int il_step, int il_coun
 }
 
 template <bool STRICT, bool EMIT, bool BB>
-__device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_fc, float &vmax, int &vnan) {
+__device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vmax, int &vnan) {
     const int ny = a.ny, pitch = a.pitch, n = a.il_count;
     const long long plane = a.plane;
     // decode: ring cell (ilr, jr), its owner (ilo, jo), boundary side dr; corners chain W/E -> top/bottom
@@ -179,7 +138,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 #pragma unroll
     for (int k = 0; k < 9; ++k) me.f[k] = g[k];
     macro_from_f<STRICT>(g, me.rho, me.ux, me.uy);
-    const float ramp = __ldg(a.ramp_tab + min(ramp_fc, a.warmup));
+    const float ramp = a.ramp;
     const int igo = a.x_off + ilo, igr = a.x_off + ilr;
     cell_rest(r);
     bc_core(a.phys, dr, igr, igo, me, r, ramp);
@@ -209,14 +168,15 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, int ramp_f
 // One fused pass: pull-stream, MRT-LES collision, sponge, macroscopic update, boundary ring,
 // obstacle refill (ref:552-573 = collide_and_stream + update_macro_var + apply_bc), f_src -> f_dst.
 //
-// "Register" variant.  Interior warps: one warp = one (32 V)-cell segment of one interior column, one
-// thread = V consecutive cells in y; every access is aligned and fully coalesced, the +-1 shift of the
-// pull in y comes from the neighbouring lane by warp shuffle with one extra scalar load at each end of
-// the segment, all issued before first use; no boundary code at all.  Ring warps (their own grid rows:
-// one row behind every 32 columns for the top / bottom cells, one block of rows for the W / E columns):
-// one ring cell per lane, see above.  BB: optional half-way bounce-back obstacle mode (not the reference's).
-template <bool STRICT, bool EMIT, int V, bool BB = false>
-__global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 : LBM_MINB1))) step_kernel(const StepArgs a) {
+// Interior warps: one warp = one 64-cell segment of one interior column, one thread = 2 consecutive cells in y;
+// every access is an aligned, fully coalesced 64-bit access, the +-1 shift of the pull in y comes from the
+// neighbouring lane by warp shuffle with one extra scalar load at each end of the segment, all issued before
+// first use; no boundary code at all.  The two cells of a thread travel through the strict collision as the two
+// halves of packed fp32 pairs (Lane2).  Ring warps (their own grid rows: one row behind every 32 columns for the
+// top / bottom cells, one block of rows for the W / E columns): one ring cell per lane, see above.
+// BB: optional half-way bounce-back obstacle mode (not the reference's).
+template <bool STRICT, bool EMIT, bool BB = false>
+__global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs a) {
     // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows (columns and ring rows, see below)
     const int row = blockIdx.y + blockIdx.z * 65535;
     // Programmatic dependent launch: this grid is scheduled while the previous step drains, and waits here
@@ -245,129 +205,129 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
     const int grp = vrow / (kRingGroup + 1), grp_r = vrow - grp * (kRingGroup + 1);
     const bool tb_row = grp_r == kRingGroup;
     const int col = grp * kRingGroup + grp_r;
-    if (a.bump_ctr && blockIdx.x == 0 && row == 0 && threadIdx.x == 0) *a.ctr_out = __ldcg(a.ctr_in) + 1;  // ref:440
+    // frame_count (ref:440): the step index and the ramp come from the host as kernel arguments, so nothing on the
+    // device reads this copy -- with early start a CTA of step n+1 may run before the last ring warp of step n.
+    if (a.bump_ctr && blockIdx.x == 0 && row == 0 && threadIdx.x == 0) *a.ctr_out = a.frame;
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
     if (we_row) {
         // ------------------------------- ring warps: W / E columns and corners -----------------
         const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, __ldcg(a.ctr_in) + 1, vmax, vnan);
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, vmax, vnan);
     } else if (tb_row) {
         // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
         const int c = grp * kRingGroup + lane;
         if (blockIdx.x == 0 && threadIdx.x < 64 && c < a.il_count)
-            ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, __ldcg(a.ctr_in) + 1, vmax, vnan);
-    } else if (col < a.il_count && seg < a.nseg) {
+            ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, vmax, vnan);
+    } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
         // ------------------------------- interior warps --------------------------------------
         const int il = a.il0 + col * a.il_step;                              // local column
-        const int j0 = seg * (32 * V) + lane * V;
-        const bool lane_on = j0 < a.pitch;
-        const int ny = a.ny, pitch = a.pitch;
-        const long long plane = a.plane;
+        const int j0 = seg * kSegCells + lane * 2;                          // < pitch: the pitch is a multiple of 64
+        const int ny = a.ny;
+        const int t = il * a.pitch + j0;                                     // cell offset inside a plane (< 2^31, checked at create)
 
-        // pull (ref:254-257): fin[c][k] = f_k(i - e_kx, j0 + c - e_ky); every load issued before the first use
-        float v[9][V];
+        // pull (ref:254-257): fin[k] = f_k(i - e_kx, j - e_ky) for j = j0, j0 + 1; every load issued before the first use
+        float2 v[9];
         float edge[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const float *colp = a.src + k * plane + (long long)(il - kEx[k]) * pitch;
-#pragma unroll
-            for (int c = 0; c < V; ++c) v[k][c] = 0.f;
+            const float *p = a.srcp[k] + t;
+            v[k] = LBM_LD(reinterpret_cast<const float2 *>(p));
             edge[k] = 0.f;
-            if (lane_on) ldf<V>(colp + j0, v[k]);
-            if (kEy[k] == 1 && lane == 0 && lane_on && j0 > 0) edge[k] = LBM_LD(colp + j0 - 1);
-            if (kEy[k] == -1 && lane == 31 && j0 + V < ny) edge[k] = LBM_LD(colp + j0 + V);
+            // segment ends: the value of the neighbouring segment (seg 0 / the last one: a ring or padding cell's input, unused)
+            if (kEy[k] == 1 && lane == 0 && seg > 0) edge[k] = LBM_LD(p - 1);
+            if (kEy[k] == -1 && lane == 31) edge[k] = LBM_LD(p + 2);   // at most one float past the row: inside the allocation
         }
-        const bool live = lane_on && j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
+        const bool live = j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
         float dx = 0.f;
-        float dy[V];
-        unsigned char code[V], links[V];
-#pragma unroll
-        for (int c = 0; c < V; ++c) { dy[c] = 0.f; code[c] = 0; links[c] = 0; }
+        float2 dy = make_float2(0.f, 0.f);
+        unsigned code2 = 0;
+        unsigned char links[2] = {0, 0};
         if (live) {
             dx = __ldg(a.damp_x + il);
-            ldv<V>(a.damp_y + j0, dy);
-            // solid bits of the warp's 32 V cells = V consecutive words; a lane's V cells sit in one of them
-            const uint32_t w = __ldg(a.code_bits + (((long long)il * pitch + j0) >> 5));
-#pragma unroll
-            for (int c = 0; c < V; ++c) code[c] = (w >> ((j0 & 31) + c)) & 1u;
-            if (BB) ldcode<V>(a.links8 + (long long)il * pitch + j0, links);
+            dy = __ldg(reinterpret_cast<const float2 *>(a.damp_y + j0));
+            // solid bits of the warp's 64 cells = 2 consecutive words; a lane's 2 cells sit in one of them
+            code2 = (__ldg(a.code_bits + (t >> 5)) >> (j0 & 31)) & 3u;
+            if (BB) {
+                const uchar2 l2 = __ldg(reinterpret_cast<const uchar2 *>(a.links8 + t));
+                links[0] = l2.x;
+                links[1] = l2.y;
+            }
         }
-        float fin[V][9];
+        float fin[2][9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             if (kEy[k] == 0) {
-#pragma unroll
-                for (int c = 0; c < V; ++c) fin[c][k] = v[k][c];
+                fin[0][k] = v[k].x;
+                fin[1][k] = v[k].y;
             } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
-                float below = __shfl_up_sync(0xffffffffu, v[k][V - 1], 1);
+                float below = __shfl_up_sync(0xffffffffu, v[k].y, 1);
                 if (lane == 0) below = edge[k];
                 fin[0][k] = below;
-#pragma unroll
-                for (int c = 1; c < V; ++c) fin[c][k] = v[k][c - 1];
+                fin[1][k] = v[k].x;
             } else {                   // needs j+1: first element of the lane above
-                float above = __shfl_down_sync(0xffffffffu, v[k][0], 1);
+                float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
                 if (lane == 31) above = edge[k];
-#pragma unroll
-                for (int c = 0; c < V - 1; ++c) fin[c][k] = v[k][c + 1];
-                fin[V - 1][k] = above;
+                fin[0][k] = v[k].y;
+                fin[1][k] = above;
             }
         }
         if (live) {
-            // collide (ref:266-420); rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
-            float g[V][9], rho[V], ux[V], uy[V];
-            bool interior[V], all_interior = true, any_interior = false;
+            if (BB) {
 #pragma unroll
-            for (int c = 0; c < V; ++c) {
-                const int j = j0 + c;
-                interior[c] = (j >= 1) && (j <= ny - 2);
-                all_interior &= interior[c];
-                any_interior |= interior[c];
-                const float damp = fmaxf(dx, dy[c]);
-                if (BB && links[c]) bounce_back(a, links[c], (long long)il * pitch + j0 + c, fin[c]);
-#ifdef LBM_NOMATH   // experiment: pure streaming bound of this access pattern
+                for (int c = 0; c < 2; ++c)
+                    if (links[c]) bounce_back(a, links[c], (long long)t + c, fin[c]);
+            }
+            // collide (ref:266-420)
+            float g[2][9];
+            if (STRICT) {
+                f32x2 f2[9], g2[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) g[c][k] = fin[c][k] + damp;
-#else
-                if (STRICT) collide_strict(a.phys, fin[c], damp, g[c]);
-                else collide_fast(a.phys, fin[c], damp, g[c]);
-#endif
-                rho[c] = ux[c] = uy[c] = 0.0f;
-                if (EMIT || (code[c] & 1)) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
-                if (code[c] & 1) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
-                    ux[c] = 0.0f; uy[c] = 0.0f;
-                    if (BB) rho[c] = 1.0f;
+                for (int k = 0; k < 9; ++k) f2[k] = pack2(fin[0][k], fin[1][k]);
+                collide_strict_t<Lane2>(a.phys, f2, pack2(fmaxf(dx, dy.x), fmaxf(dx, dy.y)), g2);
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+                for (int k = 0; k < 9; ++k) unpack2(g2[k], g[0][k], g[1][k]);
+            } else {
+                collide_fast(a.phys, fin[0], fmaxf(dx, dy.x), g[0]);
+                collide_fast(a.phys, fin[1], fmaxf(dx, dy.y), g[1]);
+            }
+            // rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
+            float rho[2] = {0.f, 0.f}, ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
+            if (EMIT || code2) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool solid = (code2 >> c) & 1u;
+                    if (EMIT || solid) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+                    if (solid) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
+                        ux[c] = 0.0f; uy[c] = 0.0f;
+                        if (BB) rho[c] = 1.0f;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+                    }
                 }
             }
-            const long long o = (long long)il * pitch + j0;
-            if (all_interior) {            // the common case: one wide store per plane
+            const bool lo_int = j0 >= 1 && j0 <= ny - 2, hi_int = j0 + 1 <= ny - 2;   // interior cells (ring cells: ring warps)
+            if (lo_int && hi_int) {            // the common case: one 64-bit store per plane
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    float t[V];
-#pragma unroll
-                    for (int c = 0; c < V; ++c) t[c] = g[c][k];
-                    stv<V>(a.dst + k * plane + o, t);
-                }
+                for (int k = 0; k < 9; ++k) *reinterpret_cast<float2 *>(a.dstp[k] + t) = make_float2(g[0][k], g[1][k]);
                 if (EMIT) {
-                    stv<V>(a.rho + o, rho);
-                    stv<V>(a.ux + o, ux);
-                    stv<V>(a.uy + o, uy);
+                    *reinterpret_cast<float2 *>(a.rho + t) = make_float2(rho[0], rho[1]);
+                    *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
+                    *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
                 }
-            } else if (any_interior) {     // the vector shares a ring cell (ring warps write it) or padding: cell by cell
+            } else {                           // the pair shares a ring cell (ring warps write it) or padding: cell by cell
 #pragma unroll
-                for (int c = 0; c < V; ++c) {
-                    if (!interior[c]) continue;
+                for (int c = 0; c < 2; ++c) {
+                    if (!(c == 0 ? lo_int : hi_int)) continue;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) a.dst[k * plane + o + c] = g[c][k];
-                    if (EMIT) { a.rho[o + c] = rho[c]; a.ux[o + c] = ux[c]; a.uy[o + c] = uy[c]; }
+                    for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
+                    if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
                 }
             }
             if (EMIT) {
 #pragma unroll
-                for (int c = 0; c < V; ++c) {
-                    if (!interior[c]) continue;
+                for (int c = 0; c < 2; ++c) {
+                    if (!(c == 0 ? lo_int : hi_int)) continue;
                     const float m2 = vmag2_strict(ux[c], uy[c]);
                     vnan |= (m2 != m2);
                     vmax = fmaxf(vmax, m2);
@@ -392,6 +352,50 @@ __global__ void __launch_bounds__(kThreads, (V == 4 ? 10 : (V == 2 ? LBM_MINB2 :
             atomicAdd(a.progress, 1ULL);
         }
     }
+}
+
+// Self test of Lane2's inline division / square root (lbm_selftest_arith): random operands from the guarded box
+// against __fdiv_rn / __fsqrt_rn, bit for bit.  out[0..2] = mismatches of a / b (b in [1/8, 8]), 1 / t (t in
+// [2^-10, 2^40]) and sqrt(x).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float float_from(unsigned mant, int exp2, bool negative) {   // 1.mant * 2^exp2
+    return __uint_as_float((negative ? 0x80000000u : 0u) | ((unsigned)(exp2 + 127) << 23) | (mant & 0x7fffffu));
+}
+__global__ void selftest_arith_kernel(long long n_per_thread, unsigned long long seed, unsigned long long *out) {
+    unsigned long long st = seed + 0x632be59bd9b4e019ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long bad[3] = {0, 0, 0};
+    for (long long it = 0; it < n_per_thread; ++it) {
+        float a[2], b[2], t[2], x[2];
+        for (int l = 0; l < 2; ++l) {
+            const unsigned long long r0 = splitmix64(st), r1 = splitmix64(st), r2 = splitmix64(st);
+            // mantissas: random, or one of the hard patterns (all zeros / all ones / single bits)
+            auto mant = [](unsigned long long r) {
+                const unsigned m = (unsigned)(r >> 8) & 0x7fffffu, sel = (unsigned)r & 15u;
+                return sel == 0 ? 0u : sel == 1 ? 0x7fffffu : sel == 2 ? 0x7ffffeu : sel == 3 ? 1u : sel == 4 ? (1u << ((r >> 40) % 23)) : m;
+            };
+            b[l] = float_from(mant(r0), (int)((r0 >> 44) % 6) - 3, false);                // [1/8, 8)
+            if (b[l] > 8.0f) b[l] = 8.0f;
+            const unsigned za = (unsigned)(r1 >> 60);
+            a[l] = za == 0 ? 0.0f : float_from(mant(r1), (int)((r1 >> 44) % 160) - 100, (r1 >> 59) & 1);   // +0 or 2^-100 .. 2^60
+            t[l] = float_from(mant(r2), (int)((r2 >> 44) % 50) - 10, false);              // [2^-10, 2^40)
+            x[l] = float_from(mant(r0 ^ r2), (int)((r1 >> 32) % 200) - 100, false);       // [2^-100, 2^100)
+        }
+        const f32x2 A = pack2(a[0], a[1]), B = pack2(b[0], b[1]), T = pack2(t[0], t[1]), X = pack2(x[0], x[1]);
+        float q0, q1;
+        unpack2(Lane2::div_refined(A, B, Lane2::rcp_refined(B)), q0, q1);
+        bad[0] += (__float_as_uint(q0) != __float_as_uint(__fdiv_rn(a[0], b[0]))) + (__float_as_uint(q1) != __float_as_uint(__fdiv_rn(a[1], b[1])));
+        unpack2(Lane2::div_refined(Lane2::bc(1.0f), T, Lane2::rcp_refined(T)), q0, q1);
+        bad[1] += (__float_as_uint(q0) != __float_as_uint(__fdiv_rn(1.0f, t[0]))) + (__float_as_uint(q1) != __float_as_uint(__fdiv_rn(1.0f, t[1])));
+        unpack2(Lane2::sqrt_inrange(X), q0, q1);
+        bad[2] += (__float_as_uint(q0) != __float_as_uint(__fsqrt_rn(x[0]))) + (__float_as_uint(q1) != __float_as_uint(__fsqrt_rn(x[1])));
+    }
+    for (int k = 0; k < 3; ++k)
+        if (bad[k]) atomicAdd(out + k, bad[k]);
 }
 
 // init(), ref:235-241: both buffers = w_k, rho = 1, u = 0; padding cells = 0.

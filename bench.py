@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--grid", default=None, help="NXxNY: urban-style obstacles on a custom grid (experiments)")
     ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e / cpu_baseline legs")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma", "register2", "register1", "async"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LBM2D_ABI_VERSION 1
+#define LBM2D_ABI_VERSION 2
 
 typedef struct LbmSolver *LbmHandle;
 
@@ -42,17 +42,16 @@ typedef enum {
 } LbmStatus;
 
 typedef enum {
-    LBM_ARITH_FAST = 0,  /* FMA + re-associated sparse transforms (production) */
-    LBM_ARITH_STRICT = 1 /* reference evaluation order, no FMA: bit-identical to the fp32 oracle */
+    LBM_ARITH_FAST = 0,  /* FMA + re-associated sparse transforms, SFU reciprocal / sqrt (tolerance-level parity) */
+    LBM_ARITH_STRICT = 1 /* reference evaluation order, every operation individually rounded, no FMA:
+                            bit-identical to the fp32 oracle */
 } LbmArith;
 
 typedef enum {
-    LBM_KERNEL_AUTO = 0,     /* the fastest measured variant (currently REGISTER2) */
-    LBM_KERNEL_REGISTER = 1, /* one warp per 128-cell column segment, float4 loads + warp shuffles */
-    LBM_KERNEL_TMA = 2,      /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
-    LBM_KERNEL_REGISTER2 = 3, /* register variant, 2 cells per thread (64-bit accesses, higher occupancy) */
-    LBM_KERNEL_REGISTER1 = 4, /* register variant, 1 cell per thread */
-    LBM_KERNEL_ASYNC = 5      /* persistent warps with private cp.async shared-memory rings (prefetch 2 segments ahead) */
+    LBM_KERNEL_AUTO = 0,     /* the fastest measured variant (REGISTER) */
+    LBM_KERNEL_REGISTER = 1, /* one warp per 64-cell column segment, 2 cells per thread: 64-bit accesses, warp shuffles for
+                                the y shift, packed fp32 pairs (FADD2) in the strict collision */
+    LBM_KERNEL_TMA = 2       /* persistent CTAs, cp.async.bulk.tensor tiles through shared memory, mbarrier pipeline */
 } LbmKernel;
 
 typedef enum {
@@ -181,6 +180,12 @@ int lbm_device_view(LbmHandle h, LbmDeviceView *out);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int lbm_launch_count(LbmHandle h, int64_t *launches);
+
+/* Self test of the strict kernel's inline packed division / square root (two cells per FFMA2 pair) against CUDA's
+ * correctly rounded __fdiv_rn / __fsqrt_rn on `pairs` random operand pairs from the range the kernel admits to the
+ * inline sequences; mismatches[0..2] = a / b, 1 / t, sqrt(x).  No reference counterpart: it guards the bit-exactness
+ * claim of LBM_ARITH_STRICT against ref:281-284, 348-356. */
+int lbm_selftest_arith(int64_t pairs, uint64_t seed, int64_t mismatches[3]);
 
 #ifdef __cplusplus
 }

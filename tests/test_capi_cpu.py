@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = pkg.load_library()
     for name in _declared_functions():
         assert hasattr(lib, name), name
-    assert lib.lbm_abi_version() == 1
+    assert lib.lbm_abi_version() == 2
 
 
 def test_library_is_sm100a_only_and_has_no_cpu_path():
@@ -39,8 +39,9 @@ def test_library_is_sm100a_only_and_has_no_cpu_path():
 
 
 def test_sass_shows_the_blackwell_paths_that_are_claimed():
-    """TMA variant: UTMALDG / UTMASTG + mbarrier (SYNCS); async variant: LDGSTS; default kernel: 64-bit L1-bypassing
-    loads, warp shuffles, no local memory; PDL: ACQBULK / griddepcontrol lowered into the step kernel."""
+    """TMA variant: UTMALDG / UTMASTG + mbarrier (SYNCS); default kernel: 64-bit L1-bypassing loads, warp shuffles, no
+    local memory; PDL: ACQBULK / griddepcontrol lowered into the step kernel; strict kernel: packed fp32 adds (FADD2),
+    and NO contracted multiply-add outside the division / square-root sequences."""
     sass = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True).stdout
     funcs = {}
     cur = None
@@ -56,14 +57,20 @@ def test_sass_shows_the_blackwell_paths_that_are_claimed():
         return "\n".join(funcs[names[0]])
     tma = body("step_tma_kernelILb0ELb0E")
     assert "UTMALDG" in tma and "UTMASTG" in tma and "SYNCS" in tma
-    assert "LDGSTS" in body("step_async_kernelILb0ELb0E")
-    hot = body("step_kernelILb0ELb0ELi2E")
+    hot = body("step_kernelILb0ELb0ELb0E")
     assert "LDG.E.64.STRONG.GPU" in hot and "SHFL" in hot and "STG.E.64" in hot
     assert "STL" not in hot and "LDL" not in hot, "the default step kernel must not touch local memory"
     # programmatic dependent launch (griddepcontrol.wait) and the early-start progress counter (acquire load that
     # invalidates L1, release = barrier + fence + 64-bit reduction)
     assert "ACQBULK" in hot and "CCTL.IVALL" in hot and "MEMBAR" in hot
     assert "RED.E.ADD.64" in hot or "ATOMG.E.ADD.64" in hot
+    # strict arithmetic: two cells per packed pair; ptxas contracts FMUL2 + FADD2 into FFMA2 even with .rn
+    # modifiers, which would change the rounding, so the multiplications are scalar: no FMUL2, and the only FFMA2 are
+    # the 19 of the inline division / square-root sequences (2 + 3 + 3 | 2 | 3 | 2 | 2 + 2: Lane2 in lbm2d_device.cuh)
+    for name in ("step_kernelILb1ELb0ELb0E", "step_kernelILb1ELb1ELb0E", "step_kernelILb1ELb0ELb1E"):
+        strict = body(name)
+        assert strict.count("FADD2") > 100, name
+        assert strict.count("FFMA2") == 19 and "FMUL2" not in strict, (name, strict.count("FFMA2"))
 
 
 def test_struct_layout_matches_c(tmp_path):

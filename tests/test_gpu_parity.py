@@ -71,8 +71,22 @@ def _assert_close(s, ref, ref64, tol=TOL, tag=""):
     return errs
 
 
+# ------------------------------------------------------------------ the strict kernel's inline division / square root
+def test_packed_division_matches_fdiv_rn():
+    """Lane2's FFMA2 Newton sequences (two cells per instruction) against __fdiv_rn / __fsqrt_rn, bit for bit, on
+    2 x 10^9 random operand pairs from the guarded range, hard mantissa patterns included."""
+    import ctypes as C
+
+    capi = importlib.import_module("01-lbm-2d_b200._capi")
+    lib = capi.load()
+    for seed in (1, 2):
+        bad = (C.c_int64 * 3)()
+        capi.check(lib.lbm_selftest_arith(1_000_000_000, seed, bad))
+        assert list(bad) == [0, 0, 0], list(bad)
+
+
 # ------------------------------------------------------------------ golden vectors (reference under shim)
-KERNELS = ("register", "tma", "register2", "register1", "async")
+KERNELS = ("register", "tma")
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -199,7 +213,7 @@ def test_very_long_domain_uses_the_z_dimension_of_the_grid(pkg):
     ref = OracleLBMC(cfg, mask)
     ref.init()
     ref.run_step(25)
-    for kernel in ("register2", "register"):
+    for kernel in ("register",):
         s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="strict", kernel=kernel)
         s.init()
         s.run_step(25)
@@ -326,7 +340,7 @@ def test_early_start_is_bit_identical_to_full_serialisation(pkg, arith, nx, ny, 
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=arith, kernel="register2")
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=arith, kernel="register")
         s.init()
         for n in (7, 200, 1, 2, 190):
             s.run_step(n)
