@@ -36,6 +36,7 @@ class LbmDeviceView(C.Structure):
 
 ABI_VERSION = 2  # LBM2D_ABI_VERSION of include/lbm2d.h
 COMM_ID_BYTES = 128
+PEER_HANDLE_BYTES = 256
 ARITH = {"fast": 0, "strict": 1}
 KERNEL = {"auto": 0, "register": 1, "tma": 2}
 EXPORTS = {
@@ -62,9 +63,13 @@ EXPORTS = {
     "lbm_export_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "lbm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lbm_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),
     "lbm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_selftest_arith": (C.c_int, [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
+    "lbm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lbm_host_free": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -112,7 +112,7 @@ def _gpu_runner(name, cfg, mask, out_dir, device, max_steps, progress):
 
 
 def _remove_outputs(out_dir, name):
-    for ext in (".h5", ".npz"):   # case_executor.py:_cleanup_failed_outputs
+    for ext in (".h5", ".npz", ".turbulence.f32"):   # case_executor.py:_cleanup_failed_outputs
         try:
             os.remove(os.path.join(out_dir, name + ext))
         except OSError:

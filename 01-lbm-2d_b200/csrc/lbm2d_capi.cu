@@ -79,6 +79,13 @@ struct LbmSolver {
     LbmParams p{};
     nccl::Comm comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory halo path (lbm_peer_connect): neighbour buffers mapped through CUDA IPC
+    bool peer_mode = false;
+    bool halo_wait_pending = false;
+    void *peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [side][f0, f1, inbox] as opened
+    int peer_nx_local[2] = {0, 0};
+    unsigned long long *inbox = nullptr;      // [0] from the west neighbour, [1] from the east neighbour, [2] error flag (low 32 bits)
+    int64_t steps_total = 0;                  // steps since creation (never reset: the inbox counters are cumulative)
     cudaStream_t stream_e = nullptr;   // edge columns + halo exchange, overlapped with the interior
     cudaEvent_t ev_m = nullptr, ev_e = nullptr, ev_e_prev = nullptr, ev_x = nullptr;
     bool ev_e_prev_valid = false;
@@ -135,6 +142,9 @@ struct LbmSolver {
 
     ~LbmSolver() {
         cudaSetDevice(device);
+        for (int side = 0; side < 2; ++side)
+            for (int i = 0; i < 3; ++i)
+                if (peer_base[side][i]) cudaIpcCloseMemHandle(peer_base[side][i]);
         if (comm) nccl::api().CommDestroy(comm);
         for (cudaEvent_t ev : {ev_m, ev_e, ev_e_prev, ev_x})
             if (ev) cudaEventDestroy(ev);
@@ -144,7 +154,7 @@ struct LbmSolver {
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
                           (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount,
-                          (void *)progress, (void *)code_bits, (void *)links8})
+                          (void *)progress, (void *)code_bits, (void *)links8, (void *)inbox})
             if (ptr) cudaFree(ptr);
         for (int i = 0; i < 2; ++i) {
             if (pinned[i]) cudaFreeHost(pinned[i]);
@@ -174,7 +184,13 @@ int ensure_staging(LbmSolver *s, size_t floats) {
 // a multi-threaded copy (and first touch) of chunk i into the caller's array.
 constexpr size_t kPinChunk = 32u << 20;
 int d2h(LbmSolver *s, void *host, const void *dev, size_t bytes) {
-    if (bytes < 2 * kPinChunk) {
+    bool pinned_dst = false;
+    if (bytes >= 2 * kPinChunk) {   // destination from lbm_host_alloc (the binding's frame pool): plain DMA at PCIe speed
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, host) == cudaSuccess) pinned_dst = at.type == cudaMemoryTypeHost;
+        else (void)cudaGetLastError();
+    }
+    if (bytes < 2 * kPinChunk || pinned_dst) {
         CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         return LBM_OK;
@@ -275,7 +291,27 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.bump_ctr = 1;
     a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, s->nx_local, s->ny, a.west_ring, a.east_ring);
     a.progress = s->progress;
+    a.col_split = -1;
+    a.edge_il[0] = a.edge_il[1] = -1;
     a.phys = s->phys;
+    if (s->peer_mode) {
+        // grid order [1 .. E | W/E ring block | nx_local - 2 | E + 1 .. nx_local - 3] (set by lbm_run through col_split)
+        static const int halo_plane[2][3] = {{3, 6, 7}, {1, 5, 8}};
+        for (int side = 0; side < 2; ++side) {
+            if (!s->peer_base[side][0]) continue;
+            a.edge_il[side] = side == 0 ? 1 : s->nx_local - 2;
+            const int nb_nx = s->peer_nx_local[side];
+            const long long nb_plane = (long long)nb_nx * s->pitch;
+            float *nb_dst = (float *)s->peer_base[side][par ^ 1];
+            const long long halo_col = side == 0 ? (long long)(nb_nx - 1) * s->pitch : 0;   // west neighbour's EAST halo / east neighbour's WEST halo
+            for (int q = 0; q < 3; ++q) a.peer_dst[side][q] = nb_dst + halo_plane[side][q] * nb_plane + halo_col;
+            a.peer_inbox[side] = (unsigned long long *)s->peer_base[side][2] + (side == 0 ? 1 : 0);   // I am its east / west neighbour
+        }
+        a.inbox = s->inbox;
+        a.peer_error = (unsigned *)(s->inbox + 2);
+        const int gx = (s->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
+        a.inbox_expected = (unsigned long long)s->steps_total * (unsigned long long)(gx + 1);   // edge column CTAs + its ring row CTA, per step
+    }
     return a;
 }
 
@@ -556,6 +592,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     CREATE_TRY(cudaMalloc(&s->progress, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(s->progress, 0, sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&s->maxv, 2 * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&s->inbox, 4 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(s->inbox, 0, 4 * sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&s->force_partial, kForceBlocks * 2 * sizeof(double)));
     CREATE_TRY(cudaMalloc(&s->force_out, 2 * sizeof(float)));
 
@@ -698,6 +736,24 @@ int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id_bytes[L
     NCCL_TRY(n.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank;
     h->nranks = nranks;
+    if (nranks > 1) {   // NCCL sets its point-to-point channels up lazily (~1-2 s): do it here, not inside the first export / step
+        nccl::Api &na = nccl::api();
+        int *scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&scratch, 4 * sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(scratch, 0, 4 * sizeof(int), h->stream));
+        NCCL_TRY(na.GroupStart());
+        if (!h->east_ring) {
+            NCCL_TRY(na.Send(scratch, 1, nccl::kInt32, rank + 1, h->comm, h->stream));
+            NCCL_TRY(na.Recv(scratch + 1, 1, nccl::kInt32, rank + 1, h->comm, h->stream));
+        }
+        if (!h->west_ring) {
+            NCCL_TRY(na.Send(scratch + 2, 1, nccl::kInt32, rank - 1, h->comm, h->stream));
+            NCCL_TRY(na.Recv(scratch + 3, 1, nccl::kInt32, rank - 1, h->comm, h->stream));
+        }
+        NCCL_TRY(na.GroupEnd());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(scratch);
+    }
     if (nranks > 1 && !std::getenv("LBM2D_NO_OVERLAP")) {
         int lo = 0, hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -705,6 +761,54 @@ int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id_bytes[L
         for (cudaEvent_t *ev : {&h->ev_m, &h->ev_e, &h->ev_e_prev, &h->ev_x})
             CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
+    return LBM_OK;
+}
+
+// ---- peer-memory halo path: CUDA IPC handles of this slab's buffers, exchanged by the host (torch.distributed) --------
+namespace {
+struct PeerBlob {
+    cudaIpcMemHandle_t f0, f1, inbox;
+    int32_t nx_local, pitch, device, pad;
+};
+static_assert(sizeof(PeerBlob) <= LBM_PEER_HANDLE_BYTES, "blob size");
+}  // namespace
+
+int lbm_peer_export(LbmHandle h, uint8_t out[LBM_PEER_HANDLE_BYTES]) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "out is null");
+    PeerBlob b{};
+    CUDA_TRY(cudaIpcGetMemHandle(&b.f0, h->f[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.f1, h->f[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.inbox, h->inbox));
+    b.nx_local = h->nx_local;
+    b.pitch = h->pitch;
+    b.device = h->device;
+    std::memset(out, 0, LBM_PEER_HANDLE_BYTES);
+    std::memcpy(out, &b, sizeof(b));
+    return LBM_OK;
+}
+
+int lbm_peer_connect(LbmHandle h, const uint8_t *west, const uint8_t *east) {
+    if (int rc = check_handle(h, false)) return rc;
+    if ((west != nullptr) == h->west_ring || (east != nullptr) == h->east_ring)
+        return fail(LBM_ERR_INVALID, "a neighbour blob is needed exactly on the sides that are halos");
+    if (h->use_tma || h->links8) return fail(LBM_ERR_INVALID, "peer-memory halos: register kernel, refill obstacle mode");
+    const uint8_t *blobs[2] = {west, east};
+    for (int side = 0; side < 2; ++side) {
+        if (!blobs[side]) continue;
+        PeerBlob b;
+        std::memcpy(&b, blobs[side], sizeof(b));
+        if (b.pitch != h->pitch || b.nx_local < 3) return fail(LBM_ERR_INVALID, "neighbour slab has a different ny / is too narrow");
+        int can = 0;
+        if (b.device != h->device) {
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+            if (!can) return fail(LBM_ERR_CUDA, "no peer access between the GPUs of neighbouring slabs");
+        }
+        const cudaIpcMemHandle_t *hs[3] = {&b.f0, &b.f1, &b.inbox};
+        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaIpcOpenMemHandle(&h->peer_base[side][i], *hs[i], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_nx_local[side] = b.nx_local;
+    }
+    h->peer_mode = true;
     return LBM_OK;
 }
 
@@ -760,7 +864,7 @@ int lbm_run(LbmHandle h, int steps) {
     {
         const int gx = (h->nseg + lbm::kWarpsPerBlock - 1) / lbm::kWarpsPerBlock;
         const int want = std::min((h->early_target + gx - 1) / gx, ncols / 3) / lbm::kRingGroup * lbm::kRingGroup;  // whole groups
-        const bool single = !(h->comm && h->nranks > 1);
+        const bool single = !(h->comm && h->nranks > 1) || h->peer_mode;   // one launch per step
         // below ~2 waves of CTAs the previous step's first columns are not done when its last CTAs start: the
         // check would always fall through to the wait and the counter update would only lengthen the step
         const long long total_ctas = (long long)ncols * gx;
@@ -769,7 +873,9 @@ int lbm_run(LbmHandle h, int steps) {
     lbm::StepArgs a_all = make_args(h);
     unsigned long long signals_all = 0;
     const dim3 blocks_all = grid_for(a_all, early_cols, &signals_all);
-    if (h->comm && h->nranks > 1 && h->stream_e) {  // the side stream starts behind everything already queued
+    // peer-memory slabs: the east edge column sits right behind the early block (see StepArgs::col_split)
+    const int col_split = (h->peer_mode && h->peer_base[1][0]) ? early_cols : -1;
+    if (!h->peer_mode && h->comm && h->nranks > 1 && h->stream_e) {  // the side stream starts behind everything already queued
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
     }
@@ -793,12 +899,15 @@ int lbm_run(LbmHandle h, int steps) {
                 else lbm::step_tma_kernel<false, false><<<grid, block, sm, h->stream>>>(ms, mh, h->map_code, md, h->map_mac, ta);
             }
             h->steps_done++;
+            h->steps_total++;
             h->launches++;
             if (int rc = exchange_halos(h, h->f[par ^ 1], h->stream)) return rc;
             continue;
         }
         lbm::StepArgs a = make_args(h);
-        const bool overlap = h->comm && h->nranks > 1 && h->nx_local >= 6 && h->stream_e;
+        if (col_split >= 0) { a.col_split = col_split; }
+        else if (h->peer_mode) { a.col_split = ncols; }   // identity order il = 1 + col
+        const bool overlap = !h->peer_mode && h->comm && h->nranks > 1 && h->nx_local >= 6 && h->stream_e;
         cudaStream_t st = h->stream;
         dim3 blocks = blocks_all;
         a.n_ring = a_all.n_ring; a.ring_row0 = a_all.ring_row0; a.ring_rows = a_all.ring_rows; a.low_rows = a_all.low_rows;
@@ -829,14 +938,18 @@ int lbm_run(LbmHandle h, int steps) {
             if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;
+        h->steps_total++;
         h->launches++;
         if (overlap) {
             CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
             std::swap(h->ev_e, h->ev_e_prev);   // interior(n+1) waits on edge(n)
             h->ev_e_prev_valid = true;
-        } else if (int rc = exchange_halos(h, a.dst, h->stream)) return rc;
+        } else if (!h->peer_mode) {
+            if (int rc = exchange_halos(h, a.dst, h->stream)) return rc;
+        }
     }
-    if (h->comm && h->nranks > 1 && h->stream_e) {  // later work on the main stream sees the last exchange
+    if (h->peer_mode && steps > 0) h->halo_wait_pending = true;   // see halo_ready()
+    if (!h->peer_mode && h->comm && h->nranks > 1 && h->stream_e) {  // later work on the main stream sees the last exchange
         CUDA_TRY(cudaEventRecord(h->ev_x, h->stream_e));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_x, 0));
     }
@@ -844,10 +957,32 @@ int lbm_run(LbmHandle h, int steps) {
     return LBM_OK;
 }
 
+// peer-memory slabs: kernels that read the halo columns of the CURRENT buffer (force links, exports of solid cells) must
+// run behind the neighbours' stores of the final step; the step kernels themselves wait in their edge CTAs.
+static int halo_ready(LbmHandle h) {
+    if (!h->peer_mode || !h->halo_wait_pending) return LBM_OK;
+    lbm::StepArgs w = make_args(h);
+    lbm::halo_wait_kernel<<<1, 32, 0, h->stream>>>(w);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    h->halo_wait_pending = false;
+    return LBM_OK;
+}
+
+// peer-memory slabs: a halo wait that timed out (a neighbour died or fell 2 s behind) poisons the run; say so.
+static int check_peer_error(LbmHandle h) {
+    if (!h->peer_mode) return LBM_OK;
+    unsigned long long flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->inbox + 2, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (flag & 0xffffffffULL) return fail(LBM_ERR_NCCL, "peer-memory halo exchange: a neighbour's halo column did not arrive within 2 s");
+    return LBM_OK;
+}
+
 int lbm_synchronize(LbmHandle h) {
     if (int rc = check_handle(h, false)) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return check_peer_error(h);
 }
 
 int lbm_step_count(LbmHandle h, int64_t *steps) {
@@ -865,6 +1000,7 @@ int lbm_get_force(LbmHandle h, float out_xy[2]) {
     if (!out_xy) return fail(LBM_ERR_INVALID, "out is null");
     out_xy[0] = out_xy[1] = 0.0f;
     if (h->n_links == 0) return lbm_synchronize(h);
+    if (int rc = halo_ready(h)) return rc;
     const int par = (int)(h->steps_done & 1);
     lbm::force_kernel<<<kForceBlocks, 256, 0, h->stream>>>(h->f[par], h->plane, h->links, h->n_links, h->force_partial);
     lbm::force_final_kernel<<<1, 32, 0, h->stream>>>(h->force_partial, kForceBlocks, h->force_out);
@@ -884,7 +1020,7 @@ int lbm_get_max_velocity(LbmHandle h, float *out) {
     float m2;
     std::memcpy(&m2, &v[0], sizeof(float));
     *out = v[1] ? NAN : std::sqrt(m2);  // max of sqrt == sqrt of max (ref:652-653)
-    return LBM_OK;
+    return check_peer_error(h);
 }
 
 static int get_planes(LbmHandle h, const float *p0, const float *p1, int nch, float *out) {
@@ -919,6 +1055,7 @@ static int export9(LbmHandle h, int mode, float *out) {
     if (!out) return fail(LBM_ERR_INVALID, "out is null");
     const size_t n = (size_t)h->p.nx * h->ny * 9;
     if (int rc = ensure_staging(h, n)) return rc;
+    if (int rc = halo_ready(h)) return rc;
     const lbm::ExportArgs a = make_export_args(h);
     dim3 grid(h->p.nx, (h->ny + 127) / 128);
     lbm::export9_kernel<<<grid, 128, 0, h->stream>>>(a, mode, h->staging);
@@ -1084,6 +1221,7 @@ int lbm_export_layout(LbmHandle h, int32_t *dlo, int32_t *dhi, int32_t *target_h
 int lbm_export_frame(LbmHandle h, float *out_chw) {
     if (int rc = check_handle(h, true)) return rc;
     if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
+    if (int rc = halo_ready(h)) return rc;
     const lbm::ExportGeom g = h->exp_geom;
     const lbm::ExportArgs a = make_export_args(h);
     const int twl = g.dhi - g.dlo;
@@ -1173,6 +1311,17 @@ int lbm_device_view(LbmHandle h, LbmDeviceView *out) {
     out->pitch = h->pitch;
     out->plane_stride = h->plane;
     out->stream = (void *)h->stream;
+    return LBM_OK;
+}
+
+int lbm_host_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return fail(LBM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return LBM_OK;
+}
+
+int lbm_host_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
     return LBM_OK;
 }
 

@@ -57,8 +57,50 @@ struct StepArgs {
     unsigned long long *progress;
     unsigned long long progress_expected;   // counter value once the previous step's rows [0, low_rows) are complete
     const RingCtx *ring;            // rare-path context in global memory (dst-specific; TMA variant)
+    // Column order of the grid: col < col_split -> il = 1 + col; col == col_split -> il = nx_local - 2 (the east edge
+    // column of a slab, see below); col > col_split -> il = col.  Single GPU / NCCL launches: il0 + col * il_step
+    // (col_split < 0).
+    int col_split;
+    // x-slabs over peer memory (lbm_peer_connect): the CTAs of an edge column -- the first / last owned column next to a
+    // halo -- also store the three populations that stream across the interface straight into the neighbour's halo
+    // column (NVLink peer stores), then add 1 to the neighbour's inbox counter (system-scope release); before they
+    // touch their own halo they wait until their inbox shows that the neighbour's edge CTAs of the PREVIOUS step are
+    // done (which also means the neighbour no longer reads the halo column this step overwrites).  side 0 = west.
+    int edge_il[2];                       // local column of the edge on that side, or -1 (domain boundary / no peer mode)
+    float *peer_dst[2][3];                // neighbour's halo column in ITS destination buffer, planes kHaloPlane[side][.]
+    unsigned long long *peer_inbox[2];    // the neighbour's counter this rank adds to
+    const unsigned long long *inbox;      // this rank's counters [2]: written by the west / east neighbour
+    unsigned long long inbox_expected;    // value once the neighbour's edge CTAs of the previous step have all signalled
+    unsigned *peer_error;                 // set if a wait timed out (the step then continues on stale data; host reports it)
     Physics phys;
 };
+
+// populations that stream across an interface: side 0 (to the west neighbour) e_x = -1, side 1 (to the east) e_x = +1
+__device__ constexpr int kHaloPlane[2][3] = {{3, 6, 7}, {1, 5, 8}};
+
+__device__ __forceinline__ int col_to_il(const StepArgs &a, int col) {
+    if (a.col_split < 0) return a.il0 + col * a.il_step;
+    return col < a.col_split ? 1 + col : (col == a.col_split ? a.nx_local - 2 : col);
+}
+
+// Wait (one thread) until this rank's inbox from `side` reaches `expected`; bounded: ~2 s, then flag an error.
+__device__ __forceinline__ void inbox_wait(const StepArgs &a, int side) {
+    unsigned long long seen, t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.inbox + side) : "memory");
+        if (seen >= a.inbox_expected) return;
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ULL) {
+                atomicExch(a.peer_error, 1u);
+                return;
+            }
+        }
+        __nanosleep(64);
+    }
+}
 
 __device__ __forceinline__ float vmag2_strict(float ux, float uy) {
     return __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy));
@@ -106,7 +148,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vma
     int ilr, jr, ilo, jo, dr, corner_dr = -1;
     if (idx < 2 * n) {
         const bool top = idx < n;
-        ilo = ilr = a.il0 + (top ? idx : idx - n) * a.il_step;
+        ilo = ilr = col_to_il(a, top ? idx : idx - n);
         jo = top ? ny - 2 : 1;
         jr = top ? ny - 1 : 0;
         dr = top ? 1 : 3;
@@ -155,6 +197,12 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vma
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.dst[k * plane + o] = r.f[k];
+#pragma unroll
+    for (int side = 0; side < 2; ++side)   // top / bottom cell of an edge column: also part of the neighbour's halo column
+        if (ilr == a.edge_il[side]) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) a.peer_dst[side][q][jr] = r.f[kHaloPlane[side][q]];
+        }
     if (EMIT) {
         a.rho[o] = r.rho;
         a.ux[o] = r.ux;
@@ -210,6 +258,17 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
     if (a.bump_ctr && blockIdx.x == 0 && row == 0 && threadIdx.x == 0) *a.ctr_out = a.frame;
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
+    // slab edge column (CTA-uniform; both false off the peer-memory slab path): wait for the neighbour's previous step
+    const bool col_cta = !we_row && !tb_row && col < a.il_count;
+    const int il_cta = col_cta ? col_to_il(a, col) : -2;
+    const bool edge_w = il_cta == a.edge_il[0], edge_e = il_cta == a.edge_il[1];
+    if (edge_w || edge_e) {
+        if (threadIdx.x == 0) {
+            if (edge_w) inbox_wait(a, 0);
+            if (edge_e) inbox_wait(a, 1);
+        }
+        __syncthreads();
+    }
     if (we_row) {
         // ------------------------------- ring warps: W / E columns and corners -----------------
         const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
@@ -217,11 +276,37 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
     } else if (tb_row) {
         // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
         const int c = grp * kRingGroup + lane;
-        if (blockIdx.x == 0 && threadIdx.x < 64 && c < a.il_count)
-            ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, vmax, vnan);
+        if (blockIdx.x == 0) {
+            // does this group hold an edge column?  (CTA-uniform)  Its ring cells read the halo and go to the neighbour too.
+            const int c0 = grp * kRingGroup, c1 = min(c0 + kRingGroup, a.il_count);
+            bool edge_here[2];
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                edge_here[side] = false;
+                if (a.edge_il[side] >= 0)
+                    for (int cc = c0; cc < c1; ++cc) edge_here[side] |= col_to_il(a, cc) == a.edge_il[side];
+            }
+            if (edge_here[0] || edge_here[1]) {
+                if (threadIdx.x == 0) {
+                    if (edge_here[0]) inbox_wait(a, 0);
+                    if (edge_here[1]) inbox_wait(a, 1);
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x < 64 && c < a.il_count)
+                ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, vmax, vnan);
+            if (edge_here[0] || edge_here[1]) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence_system();
+                    if (edge_here[0]) atomicAdd_system(a.peer_inbox[0], 1ULL);
+                    if (edge_here[1]) atomicAdd_system(a.peer_inbox[1], 1ULL);
+                }
+            }
+        }
     } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
         // ------------------------------- interior warps --------------------------------------
-        const int il = a.il0 + col * a.il_step;                              // local column
+        const int il = il_cta;                                               // local column
         const int j0 = seg * kSegCells + lane * 2;                          // < pitch: the pitch is a multiple of 64
         const int ny = a.ny;
         const int t = il * a.pitch + j0;                                     // cell offset inside a plane (< 2^31, checked at create)
@@ -238,21 +323,18 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
             if (kEy[k] == 1 && lane == 0 && seg > 0) edge[k] = LBM_LD(p - 1);
             if (kEy[k] == -1 && lane == 31) edge[k] = LBM_LD(p + 2);   // at most one float past the row: inside the allocation
         }
-        const bool live = j0 < ny;  // padding lanes only feed the shuffles / the EMIT reduction
-        float dx = 0.f;
-        float2 dy = make_float2(0.f, 0.f);
-        unsigned code2 = 0;
+        // No `live` branch: lanes in the padding of the last segment (ny % 64 != 0) run the same code on the rest-state
+        // values the padding holds (init_kernel) and store nothing -- a branch here makes ptxas sink the three loads that
+        // feed no shuffle below the shuffles, i.e. behind a full memory latency (4.5 us of a 186 us step).
+        const float dx = __ldg(a.damp_x + il);
+        const float2 dy = __ldg(reinterpret_cast<const float2 *>(a.damp_y + j0));
+        // solid bits of the warp's 64 cells = 2 consecutive words; a lane's 2 cells sit in one of them
+        const unsigned code2 = (__ldg(a.code_bits + (t >> 5)) >> (j0 & 31)) & 3u;
         unsigned char links[2] = {0, 0};
-        if (live) {
-            dx = __ldg(a.damp_x + il);
-            dy = __ldg(reinterpret_cast<const float2 *>(a.damp_y + j0));
-            // solid bits of the warp's 64 cells = 2 consecutive words; a lane's 2 cells sit in one of them
-            code2 = (__ldg(a.code_bits + (t >> 5)) >> (j0 & 31)) & 3u;
-            if (BB) {
-                const uchar2 l2 = __ldg(reinterpret_cast<const uchar2 *>(a.links8 + t));
-                links[0] = l2.x;
-                links[1] = l2.y;
-            }
+        if (BB) {
+            const uchar2 l2 = __ldg(reinterpret_cast<const uchar2 *>(a.links8 + t));
+            links[0] = l2.x;
+            links[1] = l2.y;
         }
         float fin[2][9];
 #pragma unroll
@@ -272,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
                 fin[1][k] = above;
             }
         }
-        if (live) {
+        {
             if (BB) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
@@ -315,13 +397,29 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
                     *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
                     *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
                 }
-            } else {                           // the pair shares a ring cell (ring warps write it) or padding: cell by cell
+            } else if (lo_int || hi_int) {     // the pair shares a ring cell (ring warps write it) or padding: cell by cell
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if (!(c == 0 ? lo_int : hi_int)) continue;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
                     if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
+                }
+            }
+            if (edge_w || edge_e) {            // the neighbour's halo column: the same cells, the three planes it will pull
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    if (!(side == 0 ? edge_w : edge_e)) continue;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int k = kHaloPlane[side][q];
+                        float *p = a.peer_dst[side][q] + j0;
+                        if (lo_int && hi_int) *reinterpret_cast<float2 *>(p) = make_float2(g[0][k], g[1][k]);
+                        else {
+                            if (lo_int) p[0] = g[0][k];
+                            if (hi_int) p[1] = g[1][k];
+                        }
+                    }
                 }
             }
             if (EMIT) {
@@ -345,12 +443,29 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
             if (any_nan) a.maxv_bits[1] = 1u;
         }
     }
+    if (edge_w || edge_e) {   // edge-column CTA: its part of the neighbour's halo column is complete
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (edge_w) atomicAdd_system(a.peer_inbox[0], 1ULL);
+            if (edge_e) atomicAdd_system(a.peer_inbox[1], 1ULL);
+        }
+    }
     if (row < a.low_rows) {   // release: this CTA's part of the low rows is complete and visible device-wide
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(a.progress, 1ULL);
         }
+    }
+}
+
+// End of a batch on the peer-memory slab path: later work on the stream (force, exports) reads the halo columns of the
+// final step, which the neighbours write.
+__global__ void halo_wait_kernel(const StepArgs a) {
+    if (threadIdx.x == 0) {
+        if (a.edge_il[0] >= 0) inbox_wait(a, 0);
+        if (a.edge_il[1] >= 0) inbox_wait(a, 1);
     }
 }
 
@@ -398,16 +513,15 @@ __global__ void selftest_arith_kernel(long long n_per_thread, unsigned long long
         if (bad[k]) atomicAdd(out + k, bad[k]);
 }
 
-// init(), ref:235-241: both buffers = w_k, rho = 1, u = 0; padding cells = 0.
+// init(), ref:235-241: both buffers = w_k (padding cells included), rho = 1, u = 0.
 __global__ void init_kernel(float *f0, float *f1, float *rho, float *ux, float *uy, long long plane, int ny, int pitch) {
     const long long n = plane;
     for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
         const bool real = (int)(o % pitch) < ny;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float v = real ? kW[k] : 0.0f;
-            f0[k * plane + o] = v;
-            f1[k * plane + o] = v;
+        for (int k = 0; k < 9; ++k) {   // the padding cells keep this rest state for ever (never written again)
+            f0[k * plane + o] = kW[k];
+            f1[k * plane + o] = kW[k];
         }
         rho[o] = real ? 1.0f : 0.0f;
         ux[o] = 0.0f;

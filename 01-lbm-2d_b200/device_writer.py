@@ -8,13 +8,21 @@ where the work happens: `append_from_solver(solver)` asks the solver for the alr
 (9, H, W) frame (`lbm_export_frame`), so ~11 MB instead of the 604 MB (nx, ny, 9) array cross PCIe per
 export at 8192x2048, and the running sums live on the device until `finalize()`.
 
-HDF5 output needs h5py (as in the reference); without it the same datasets go to an .npz next to the
-requested path, so the statistics stay usable and testable.
+Like the reference, the file is opened in the constructor and every frame is appended to the resizable, chunked
+`turbulence` dataset as it arrives (writer:69, 112-119, 167-169): host memory stays at ONE frame however long the
+case runs, and a killed run leaves its frames on disk.
+
+Container.  HDF5 through h5py, as in the reference (`container="h5"`).  h5py is absent from the build image, so
+there is a second, explicitly named container for such hosts: `container="raw"` streams the frames to
+`<stem>.turbulence.f32` (append-only float32) and writes the remaining datasets and attributes to `<stem>.npz` at
+`finalize()`; `read_case()` reads either back into the same dict.  `container="auto"` (default) picks h5 when h5py
+imports and raw otherwise, and says so once on stderr -- the raw container is a fallback, not the format.
 """
 from __future__ import annotations
 
 import json
 import os
+import sys
 
 import numpy as np
 
@@ -23,9 +31,93 @@ try:
 except Exception:  # pragma: no cover - h5py is absent from the build image
     h5py = None
 
+_warned = False
+
+
+class _H5Container:
+    """writer:69-133: file opened up front, `static_mask` written at once, `turbulence` resizable + chunked."""
+
+    def __init__(self, path, channels, th, tw, compression, static_mask):
+        self.path = path
+        self.f = h5py.File(path, "w", libver="latest")
+        if static_mask is not None:
+            self.f.create_dataset("static_mask", data=static_mask, dtype="f4", compression=compression)
+        self.dset = self.f.create_dataset("turbulence", shape=(0, channels, th, tw), maxshape=(None, channels, th, tw),
+                                          dtype="f4", compression=compression, chunks=(1, channels, th, tw))
+
+    def append(self, frame):
+        n = self.dset.shape[0]
+        self.dset.resize(n + 1, axis=0)
+        self.dset[n] = frame
+
+    def finalize(self, datasets, attrs):
+        for k, v in datasets.items():
+            self.f.create_dataset(k, data=v)
+        for k, v in attrs.items():
+            self.f.attrs[k] = v
+        self.f.close()
+
+    def abort(self):
+        self.f.close()
+
+
+class _RawContainer:
+    """h5py-free streaming container: frames appended to <stem>.turbulence.f32, the rest in <stem>.npz."""
+
+    def __init__(self, path, channels, th, tw, compression, static_mask):
+        self.stem = os.path.splitext(path)[0]
+        self.shape = (channels, th, tw)
+        self.static_mask = static_mask
+        self.n = 0
+        self.fh = open(self.stem + ".turbulence.f32", "wb")
+
+    def append(self, frame):
+        self.fh.write(np.ascontiguousarray(frame, np.float32).tobytes())
+        self.fh.flush()
+        self.n += 1
+
+    def finalize(self, datasets, attrs):
+        self.fh.close()
+        extra = {} if self.static_mask is None else {"static_mask": self.static_mask}
+        np.savez(self.stem + ".npz", turbulence_shape=np.array((self.n,) + self.shape, np.int64), **extra, **datasets,
+                 **{f"attr_{k}": np.asarray(v) for k, v in attrs.items()})
+
+    def abort(self):
+        self.fh.close()
+
+
+def read_case(path):
+    """Datasets (+ `attrs`) of a finished case as a dict, from whichever container `path` (with or without extension)
+    was written to.  `turbulence` comes back as an array for h5 and as a read-only memmap for the raw container."""
+    stem = os.path.splitext(path)[0] if path.endswith((".h5", ".npz")) else path
+    if h5py is not None and os.path.exists(stem + ".h5"):
+        with h5py.File(stem + ".h5", "r") as f:
+            out = {k: f[k][...] for k in f.keys()}
+            out["attrs"] = {k: f.attrs[k] for k in f.attrs.keys()}
+        return out
+    z = np.load(stem + ".npz")
+    out = {k: z[k] for k in z.files if not k.startswith("attr_") and k != "turbulence_shape"}
+    shape = tuple(int(v) for v in z["turbulence_shape"])
+    out["turbulence"] = (np.memmap(stem + ".turbulence.f32", np.float32, "r", shape=shape) if shape[0] > 0
+                         else np.zeros(shape, np.float32))
+    out["attrs"] = {k[5:]: z[k] for k in z.files if k.startswith("attr_")}
+    return out
+
+
+def static_mask_host(mask, x0, x1, y0, y1, target_w, target_h):
+    """writer:74-110: nearest-resized ROI mask + signed distance field (fluid positive) -> (2, H, W) float32."""
+    import cv2
+    import scipy.ndimage
+
+    hw = np.asarray(mask)[x0:x1, y0:y1].transpose(1, 0).astype(np.float32)
+    small = cv2.resize(hw, (target_w, target_h), interpolation=cv2.INTER_NEAREST)
+    small = (small > 0.5).astype(np.float32)
+    sdf = scipy.ndimage.distance_transform_edt(1 - small) - scipy.ndimage.distance_transform_edt(small)
+    return np.stack([small, sdf], axis=0).astype(np.float32)
+
 
 class DeviceLBMCaseWriter:
-    def __init__(self, file_path, config, nx, ny, channels=9, mask_data=None, solver=None):
+    def __init__(self, file_path, config, nx, ny, channels=9, mask_data=None, solver=None, container="auto"):
         os.makedirs(os.path.dirname(os.path.abspath(file_path)), exist_ok=True)
         self.file_path, self.config, self.nx, self.ny, self.channels = file_path, config, nx, ny, channels
         self.is_closed = False
@@ -41,91 +133,105 @@ class DeviceLBMCaseWriter:
         scale = save_res_h / self.crop_h                                   # writer:55-58
         self.target_w, self.target_h = int(self.crop_w * scale), save_res_h
         self.compression = config["outputs"]["dataset"]["compression"]
-        self.frames = []
-        self.static_mask = None
-        if mask_data is not None:
-            self.static_mask = self._static_mask(np.asarray(mask_data))
+        self.n_frames = 0
+        self.last_frame = None
         self._solver = None
+        self._mask = None if mask_data is None else np.asarray(mask_data)
+        self._container_kind = self._pick_container(container)
+        self._container = None
+        self.static_mask = None
+        self.result, self.attrs = None, None
         if solver is not None:
             self.attach(solver)
+        else:
+            self._open()
+
+    @staticmethod
+    def _pick_container(kind):
+        global _warned
+        if kind == "h5" and h5py is None:
+            raise ImportError("container='h5' needs h5py (as the reference's LBMCaseWriter does); use container='raw' "
+                              "for the h5py-free streaming container")
+        if kind == "auto":
+            kind = "h5" if h5py is not None else "raw"
+            if kind == "raw" and not _warned:
+                _warned = True
+                print("[DeviceLBMCaseWriter] h5py is not importable: writing <stem>.turbulence.f32 + <stem>.npz "
+                      "(container='raw') instead of HDF5; read with device_writer.read_case()", file=sys.stderr)
+        if kind not in ("h5", "raw"):
+            raise ValueError(f"unknown container {kind!r}")
+        return kind
+
+    def _is_writer_rank(self):
+        return getattr(self._solver, "rank", 0) == 0
+
+    def _open(self):
+        """Static mask (+ SDF) and the output file; on x-slabs rank 0 holds the file."""
+        if self._container is not None:
+            return
+        if self._mask is not None and self.static_mask is None:
+            sv = self._solver
+            if sv is not None and hasattr(sv, "static_mask_fields") and getattr(sv, "world", 1) == 1:
+                self.static_mask = sv.static_mask_fields(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
+            else:
+                self.static_mask = static_mask_host(self._mask, self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
+        if self._is_writer_rank():
+            cls = _H5Container if self._container_kind == "h5" else _RawContainer
+            self._container = cls(self.file_path, self.channels, self.target_h, self.target_w, self.compression, self.static_mask)
 
     def attach(self, solver):
         solver.export_configure(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
         self._solver = solver
-
-    def _static_mask(self, mask):
-        """writer:74-110: nearest-resized mask + signed distance field (fluid positive), host, once per case."""
-        import cv2
-        import scipy.ndimage
-
-        hw = mask[self.x0:self.x1, self.y0:self.y1].transpose(1, 0).astype(np.float32)
-        small = cv2.resize(hw, (self.target_w, self.target_h), interpolation=cv2.INTER_NEAREST)
-        small = (small > 0.5).astype(np.float32)
-        sdf = scipy.ndimage.distance_transform_edt(1 - small) - scipy.ndimage.distance_transform_edt(small)
-        return np.stack([small, sdf], axis=0).astype(np.float32)
+        self._open()
 
     def append_from_solver(self, solver=None):
         if self.is_closed:
             return
         if solver is not None and solver is not self._solver:
             self.attach(solver)
-        self.frames.append(self._solver.export_frame())
+        sv = self._solver
+        frame = sv.export_frame()
+        if getattr(sv, "world", 1) > 1:   # x-slabs: every rank holds a column range of the frame; rank 0 writes
+            frame = sv.gather_columns(frame)
+        if self._container is not None:
+            self._container.append(frame)
+        self.last_frame = frame
+        self.n_frames += 1
 
     def append(self, moment_data):
         raise TypeError("DeviceLBMCaseWriter takes frames from the solver: use append_from_solver(solver); "
                         "for host (nx, ny, 9) arrays use the reference's LBMCaseWriter")
 
     def finalize(self):
+        """writer:212-251.  Returns read_case(file_path) on the writing rank (None elsewhere / when already closed)."""
         if self.is_closed:
             return None
         self.is_closed = True
-        st = self._solver.export_stats() if self._solver is not None else {"running_count": 0}
-        frames = np.stack(self.frames, axis=0) if self.frames else None
-        if getattr(self._solver, "world", 1) > 1:
-            # x-slabs: every rank holds a column range of the global frame; assemble on rank 0
-            sv = self._solver
-            frames = sv.gather_columns(frames if frames is not None else np.zeros((0, 9, self.target_h, 0), np.float32))
+        sv = self._solver
+        st = sv.export_stats() if sv is not None else {"running_count": 0}
+        if getattr(sv, "world", 1) > 1:
             parts = {k: sv.gather_columns(st[k]) for k in ("running_sum", "running_vel_sq_sum", "sum_abs_vor")}
             mins = sv.gather_columns(st["global_min"][:, None])
             maxs = sv.gather_columns(st["global_max"][:, None])
             if sv.rank != 0:
-                self.result, self.attrs = None, None
                 return None
             st = dict(st, **parts, global_min=mins.min(axis=1), global_max=maxs.max(axis=1))
-        out = {}
-        if self.static_mask is not None:
-            out["static_mask"] = self.static_mask
+        out, attrs = {}, {}
         if st["running_count"] > 0:
             n = st["running_count"]
             mean_field = (st["running_sum"] / n).astype(np.float32)              # writer:224-233
-            out.update(
-                turbulence=frames if frames is not None else np.zeros((0, 9, self.target_h, self.target_w), np.float32),
-                mean_vel_field=mean_field,
-                mean_vel_sq_field=(st["running_vel_sq_sum"] / n).astype(np.float32),
-                sum_vor=st["sum_abs_vor"].astype(np.float32),
-            )
-            attrs = {"stats_min": st["global_min"], "stats_max": st["global_max"],
+            out.update(mean_vel_field=mean_field,
+                       mean_vel_sq_field=(st["running_vel_sq_sum"] / n).astype(np.float32),
+                       sum_vor=st["sum_abs_vor"].astype(np.float32))
+            meta = dict(self.config)
+            meta["_dataset_info"] = {"original_crop": [self.crop_w, self.crop_h], "saved_resolution": [self.target_w, self.target_h],
+                                     "resize_algo": "INTER_AREA (per channel, on device)"}
+            attrs = {"config_json": json.dumps(meta, default=str), "stats_min": st["global_min"], "stats_max": st["global_max"],
                      "stats_mean": np.mean(mean_field, axis=(1, 2))}
-        else:
-            attrs = {}
-        meta = dict(self.config)
-        meta["_dataset_info"] = {"original_crop": [self.crop_w, self.crop_h], "saved_resolution": [self.target_w, self.target_h],
-                                 "resize_algo": "INTER_AREA (per channel, on device)"}
-        attrs["config_json"] = json.dumps(meta, default=str)
-        self.result, self.attrs = out, attrs
-        if h5py is not None:
-            with h5py.File(self.file_path, "w", libver="latest") as f:
-                for k, v in out.items():
-                    kw = {"compression": self.compression} if k in ("static_mask", "turbulence") else {}
-                    if k == "turbulence":
-                        kw["chunks"] = (1, self.channels, self.target_h, self.target_w)
-                    f.create_dataset(k, data=v, **kw)
-                for k, v in attrs.items():
-                    f.attrs[k] = v
-        else:
-            np.savez(os.path.splitext(self.file_path)[0] + ".npz", **out,
-                     **{f"attr_{k}": np.asarray(v) for k, v in attrs.items()})
-        return out
+        self.attrs = attrs
+        self._container.finalize(out, attrs)
+        self.result = read_case(self.file_path)
+        return self.result
 
     def close(self):
         return self.finalize()

@@ -8,11 +8,18 @@ directions (f1,f5,f8 eastward; f3,f6,f7 westward; `ny` floats each) -- inside `l
 Boundary ownership: inlet on rank 0, outlet on the last rank, top/bottom rows on every rank.  The
 per-batch scalars (force, max|u|) are reduced here with torch.distributed.
 
-`torch.distributed` is plumbing only (rendezvous, id broadcast, two scalar reductions per batch).
+Halo transport: on NVLink / NVSwitch nodes the slabs map each other's population buffers through CUDA IPC
+(`halo="auto"` -> "peer") and the step kernel itself stores the outgoing populations into the neighbour's halo
+column and synchronises through per-step counters -- ONE launch per step, no NCCL call on the step path
+(include/lbm2d.h, lbm_peer_connect).  `halo="nccl"` keeps the grouped ncclSend/ncclRecv exchange (also the
+automatic fallback when peer access is missing).
+
+`torch.distributed` is plumbing only (rendezvous, id / handle exchange, two scalar reductions per batch).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -90,7 +97,8 @@ class SlabLBM:
     return GLOBAL values on every rank, field getters return this rank's owned columns
     (`gather_*` assemble the global array on rank 0)."""
 
-    def __init__(self, config, mask_data=None, *, rank, world, device=None, arith="fast", kernel="auto", dist=None):
+    def __init__(self, config, mask_data=None, *, rank, world, device=None, arith="strict", kernel="auto", dist=None,
+                 halo="auto"):
         if dist is None:
             import torch.distributed as dist
         self.dist, self.rank, self.world = dist, rank, world
@@ -112,13 +120,47 @@ class SlabLBM:
             dist.broadcast(t, src=0)
             ident = t.cpu().numpy()
             _capi.check(lib.lbm_comm_connect(self.solver._h, rank, world, ident.ctypes.data_as(C.c_void_p)))
+            self.halo_path = "nccl"
+            halo = os.environ.get("LBM2D_HALO", halo)   # experiments: force the NCCL exchange
+            if halo != "nccl" and self._device is not None and kernel in ("auto", "register"):
+                self._connect_peers(lib, torch)
         for name in ("nx", "ny", "Re", "name", "nu", "tau_0", "characteristic_length", "rho_in_target",
                      "rho_out_target", "C_smag", "warmup_steps"):
             setattr(self, name, getattr(self.solver, name))
         self.vel, self.rho, self.mask = self.solver.vel, self.solver.rho, self.solver.mask
 
+    def _connect_peers(self, lib, torch):
+        """Peer-memory halo path: exchange CUDA IPC handles of the population buffers, map the neighbours' (see
+        include/lbm2d.h).  All ranks take the same path: if any rank cannot map a neighbour, all keep NCCL."""
+        blob = np.zeros(_capi.PEER_HANDLE_BYTES, np.uint8)
+        _capi.check(lib.lbm_peer_export(self.solver._h, blob.ctypes.data_as(C.c_void_p)))
+        mine = torch.from_numpy(blob).to(self._device)
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allb, mine)
+        west = np.ascontiguousarray(allb[self.rank - 1].cpu().numpy()) if self.rank > 0 else None
+        east = np.ascontiguousarray(allb[self.rank + 1].cpu().numpy()) if self.rank + 1 < self.world else None
+        can = torch.ones(1, device=self._device)
+        try:   # probe first: peer access must exist towards both neighbours on every rank
+            for nb in (west, east):
+                if nb is not None:
+                    dev = int(np.frombuffer(nb[192:204].tobytes(), np.int32)[2])
+                    if dev != torch.cuda.current_device() and not torch.cuda.can_device_access_peer(torch.cuda.current_device(), dev):
+                        can.zero_()
+        except Exception:
+            can.zero_()
+        self.dist.all_reduce(can, op=self.dist.ReduceOp.MIN)
+        if can.item() < 1:
+            return
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _capi.check(lib.lbm_peer_connect(self.solver._h, p(west), p(east)))
+        self._peer_keepalive = (west, east)
+        self.halo_path = "peer"
+
     def init(self):
         self.solver.init()
+        if self.world > 1:   # nobody steps (and pushes halo columns) before every rank's buffers hold the initial state
+            self.solver.synchronize()
+            self.dist.barrier()
 
     def run_step(self, steps=1):
         self.solver.run_step(steps)
@@ -149,12 +191,30 @@ class SlabLBM:
         return self.solver.export_stats()
 
     def gather_columns(self, local):
-        """Concatenate per-rank arrays along their LAST axis (output columns) on rank 0 (None elsewhere)."""
+        """Concatenate per-rank arrays along their LAST axis (output columns) on rank 0 (None elsewhere).
+        Over NCCL the arrays travel as tensors padded to the widest rank (one collective, no pickling)."""
         if self.world == 1:
             return local
-        parts = [None] * self.world if self.rank == 0 else None
-        self.dist.gather_object(local, parts, dst=0)
-        return np.concatenate(parts, axis=-1) if self.rank == 0 else None
+        if self._device is None:   # gloo / CPU tests
+            parts = [None] * self.world if self.rank == 0 else None
+            self.dist.gather_object(local, parts, dst=0)
+            return np.concatenate(parts, axis=-1) if self.rank == 0 else None
+        import torch
+
+        local = np.ascontiguousarray(local)
+        widths = torch.zeros(self.world, dtype=torch.int64, device=self._device)
+        widths[self.rank] = local.shape[-1]
+        self.dist.all_reduce(widths)
+        widths = [int(w) for w in widths.tolist()]
+        wmax = max(max(widths), 1)
+        pad = torch.zeros(local.shape[:-1] + (wmax,), dtype=torch.from_numpy(local).dtype, device=self._device)
+        if local.shape[-1]:
+            pad[..., :local.shape[-1]] = torch.from_numpy(local).to(self._device)
+        parts = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
+        self.dist.gather(pad, parts, dst=0)
+        if self.rank != 0:
+            return None
+        return np.concatenate([p[..., :w].cpu().numpy() for p, w in zip(parts, widths)], axis=-1)
 
     def gather(self, local):
         """Concatenate per-rank owned-column arrays along x on rank 0 (None elsewhere)."""
@@ -177,4 +237,7 @@ class SlabLBM:
         return self.solver.device_view()
 
     def close(self):
+        if self.world > 1 and getattr(self, "halo_path", "nccl") == "peer":
+            self.solver.synchronize()   # a neighbour may still be pushing into this rank's halo columns
+            self.dist.barrier()
         self.solver.close()

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math as _math
+import threading
+import weakref
 
 import numpy as np
 
@@ -26,14 +28,67 @@ class _FieldShim:
         return self._getter()
 
 
+class _PinnedPool:
+    """Page-locked frame buffers behind `get_moments_numpy()`.
+
+    The reference contract (ref:739-741): every call returns a fresh array the caller owns -- the
+    run loop queues it to the writer thread (io/lbm_writer.py:260-287, queue depth 5) and immediately asks for
+    the next one.  A pageable `np.empty` destination costs first-touch page faults and a staged copy (172 ms per
+    604 MB frame at 8192x2048); here the array is a view of a pinned buffer (`lbm_host_alloc`), filled by one DMA,
+    and a finalizer returns the buffer to the pool when the LAST reference to the array (views included) is dropped.
+    Two live arrays never share memory.  `max_buffers` bounds the pinned memory (queue depth 5 + the frame being
+    written + the one being filled = 7); beyond it the call falls back to a pageable array."""
+
+    def __init__(self, lib, max_buffers=7, max_bytes=8 << 30):
+        self._lib, self._free, self._sizes = lib, {}, {}
+        self._max, self._max_bytes, self._lock = max_buffers, max_bytes, threading.Lock()
+
+    def take(self, shape):
+        nbytes = int(np.prod(shape)) * 4
+        with self._lock:
+            ptr = next((p for p in self._free.get(nbytes, [])), None)
+            if ptr is not None:
+                self._free[nbytes].remove(ptr)
+            elif len(self._sizes) < self._max and sum(self._sizes.values()) + nbytes <= self._max_bytes:
+                out = C.c_void_p()
+                if self._lib.lbm_host_alloc(nbytes, C.byref(out)) != 0:
+                    return None
+                ptr = out.value
+                self._sizes[ptr] = nbytes
+            else:
+                return None
+        buf = (C.c_float * (nbytes // 4)).from_address(ptr)
+        weakref.finalize(buf, self._give_back, ptr, nbytes)
+        return np.ctypeslib.as_array(buf).reshape(shape)   # the array's base chain keeps `buf` alive
+
+    def _give_back(self, ptr, nbytes):
+        with self._lock:
+            if ptr in self._sizes:
+                self._free.setdefault(nbytes, []).append(ptr)
+
+    def close(self):
+        """Frees the buffers that are back in the pool; buffers still owned by live arrays stay valid (and pinned)
+        until the process ends."""
+        with self._lock:
+            for lst in self._free.values():
+                for ptr in lst:
+                    self._lib.lbm_host_free(C.c_void_p(ptr))
+                    self._sizes.pop(ptr, None)
+            self._free.clear()
+            self._sizes = {}
+
+
 class LBM2D_MRT_LES:
-    def __init__(self, config, mask_data=None, *, arith="fast", kernel="auto", device=None, slab=None,
+    _PIN_THRESHOLD = 64 << 20   # bytes: frames at least this large come from the pinned pool
+
+    def __init__(self, config, mask_data=None, *, arith="strict", kernel="auto", device=None, slab=None,
                  obstacle_mode="refill"):
         """ref:13-29.  `config` is the per-case YAML dict; missing keys raise KeyError like the
         reference.  `mask_data`: bool/float (nx, ny), True/1 = solid, None = all fluid (ref:107-111).
 
-        Extensions (keyword-only, absent from the reference): `arith` = "fast" | "strict"
-        (strict is bit-identical to the fp32 oracle), `kernel` = "auto" | "register" | "tma",
+        Extensions (keyword-only, absent from the reference): `arith` = "strict" (default: every operation rounded
+        as the reference writes it, bit-identical to the fp32 oracle; 95 % of the HBM roofline) | "fast" (FMA,
+        re-associated transforms, SFU reciprocals: tolerance-level parity, ~5 % faster), `kernel` = "auto" | "register" | "tma",
         `device` = CUDA ordinal, `slab` =
         (x0, nx_owned) to own a column range of a larger global domain (multi-GPU), `obstacle_mode` =
         "refill" (the reference's wet-node refill, ref:452-455) | "bounce_back" (half-way bounce-back on the
@@ -85,6 +140,7 @@ class LBM2D_MRT_LES:
         h = C.c_void_p()
         _capi.check(self._lib.lbm_create(C.byref(p), mask_ptr, C.byref(h)))
         self._h = h
+        self._pool = None
 
         # Taichi-field look-alikes (ref:99-128); only `.to_numpy()` is supported
         self.vel = _FieldShim(lambda: self._get("lbm_get_vel", (self._nx_owned, self.ny, 2)))
@@ -153,8 +209,18 @@ class LBM2D_MRT_LES:
         return self.vel.to_numpy(), self.mask.to_numpy()
 
     def get_moments_numpy(self):
-        """ref:739-741 -> fresh (nx,ny,9) f32 array owned by the caller (it is queued to the writer thread)"""
-        return self._get("lbm_get_moments", (self._nx_owned, self.ny, 9))
+        """ref:739-741 -> fresh (nx,ny,9) f32 array owned by the caller (it is queued to the writer thread).
+        Large frames are views of pinned pool buffers filled by one DMA (see _PinnedPool)."""
+        shape = (self._nx_owned, self.ny, 9)
+        out = None
+        if int(np.prod(shape)) * 4 >= self._PIN_THRESHOLD:
+            if self._pool is None:
+                self._pool = _PinnedPool(self._lib)
+            out = self._pool.take(shape)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        _capi.check(self._lib.lbm_get_moments(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     # ------------------------------------------------------------------ on-device export reduction
     def export_configure(self, x0, x1, y0, y1, target_w, target_h):
@@ -224,6 +290,9 @@ class LBM2D_MRT_LES:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.lbm_destroy(h)
+        pool, self._pool = getattr(self, "_pool", None), None
+        if pool is not None:
+            pool.close()
 
     def __del__(self):
         try:

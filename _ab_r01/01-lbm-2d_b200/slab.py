@@ -1,0 +1,180 @@
+"""x-slab domain decomposition of one large grid over the GPUs of a node.
+
+The reference is single-device; this is what the B200 build adds.  One process per GPU
+(`torchrun`), rank r owns global columns `partition(nx, world)[r]` plus one halo column towards each
+neighbour.  Every step each interface moves the three populations that stream across it, in both
+directions (f1,f5,f8 eastward; f3,f6,f7 westward; `ny` floats each) -- inside `lbm_run`, by grouped
+`ncclSend/ncclRecv` on the solver's stream (NVLink), so a batch of N steps is still ONE host call.
+Boundary ownership: inlet on rank 0, outlet on the last rank, top/bottom rows on every rank.  The
+per-batch scalars (force, max|u|) are reduced here with torch.distributed.
+
+`torch.distributed` is plumbing only (rendezvous, id broadcast, two scalar reductions per batch).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .solver import LBM2D_MRT_LES
+
+EAST_GOING = (1, 5, 8)  # e_x = +1: pulled from column i-1, so they travel west -> east
+WEST_GOING = (3, 6, 7)
+
+
+def partition(nx: int, world: int):
+    """Contiguous column ranges [(x0, n), ...] west to east; the remainder goes to the first ranks."""
+    if world < 1 or nx < 2 * world:
+        raise ValueError(f"cannot split nx={nx} into {world} slabs of at least 2 columns")
+    base, rem = divmod(nx, world)
+    out, x0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((x0, n))
+        x0 += n
+    return out
+
+
+def halo_plan(rank: int, world: int):
+    """[(neighbour_rank, side, planes_sent, planes_received)] for this rank."""
+    plan = []
+    if rank + 1 < world:
+        plan.append((rank + 1, "E", EAST_GOING, WEST_GOING))
+    if rank > 0:
+        plan.append((rank - 1, "W", WEST_GOING, EAST_GOING))
+    return plan
+
+
+def exchange_host(dist, rank, world, pack, unpack):
+    """Host-side halo exchange (numpy through torch.distributed point-to-point; gloo on CPU).
+    `pack(side) -> (ny, 3) array`, `unpack(side, array)`.  Used by the CPU tests of the decomposition;
+    the GPU path exchanges inside lbm_run()."""
+    import torch
+
+    reqs, bufs = [], []
+    for nb, side, _, _ in halo_plan(rank, world):
+        out = torch.from_numpy(np.ascontiguousarray(pack(side)))
+        inc = torch.empty_like(out)
+        reqs.append(dist.isend(out, dst=nb))
+        reqs.append(dist.irecv(inc, src=nb))
+        bufs.append((side, inc, out))
+    for r in reqs:
+        r.wait()
+    for side, inc, _ in bufs:
+        unpack(side, inc.numpy())
+
+
+def reduce_force(dist, local_force, device=None):
+    """Sum of the per-slab momentum-exchange forces (each solid cell is owned by exactly one rank)."""
+    import torch
+
+    t = torch.tensor(np.asarray(local_force, np.float64), device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().astype(np.float32)
+
+
+def reduce_max_velocity(dist, local_max, device=None):
+    """Global max|u|; NaN on any rank gives NaN (the stability fuse relies on it)."""
+    import torch
+
+    v = float(local_max)
+    t = torch.tensor([0.0 if np.isnan(v) else v, 1.0 if np.isnan(v) else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.cpu()
+    return float("nan") if t[1].item() > 0 else float(t[0].item())
+
+
+class SlabLBM:
+    """`LBM2D_MRT_LES` for one slab of a decomposed domain: same methods; `get_force` / `get_max_velocity`
+    return GLOBAL values on every rank, field getters return this rank's owned columns
+    (`gather_*` assemble the global array on rank 0)."""
+
+    def __init__(self, config, mask_data=None, *, rank, world, device=None, arith="fast", kernel="auto", dist=None):
+        if dist is None:
+            import torch.distributed as dist
+        self.dist, self.rank, self.world = dist, rank, world
+        nx = config["simulation"]["nx"]
+        self.slabs = partition(nx, world)
+        self.x0, self.nx_owned = self.slabs[rank]
+        self.solver = LBM2D_MRT_LES(config, mask_data, arith=arith, kernel=kernel, device=device,
+                                    slab=(self.x0, self.nx_owned) if world > 1 else None)
+        self._device = None
+        if world > 1:
+            import torch
+
+            self._device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
+            lib = self.solver._lib
+            ident = np.zeros(_capi.COMM_ID_BYTES, np.uint8)
+            if rank == 0:
+                _capi.check(lib.lbm_comm_unique_id(ident.ctypes.data_as(C.c_void_p)))
+            t = torch.from_numpy(ident).to(self._device) if self._device is not None else torch.from_numpy(ident)
+            dist.broadcast(t, src=0)
+            ident = t.cpu().numpy()
+            _capi.check(lib.lbm_comm_connect(self.solver._h, rank, world, ident.ctypes.data_as(C.c_void_p)))
+        for name in ("nx", "ny", "Re", "name", "nu", "tau_0", "characteristic_length", "rho_in_target",
+                     "rho_out_target", "C_smag", "warmup_steps"):
+            setattr(self, name, getattr(self.solver, name))
+        self.vel, self.rho, self.mask = self.solver.vel, self.solver.rho, self.solver.mask
+
+    def init(self):
+        self.solver.init()
+
+    def run_step(self, steps=1):
+        self.solver.run_step(steps)
+
+    def get_force(self):
+        f = self.solver.get_force()
+        return f if self.world == 1 else reduce_force(self.dist, f, self._device)
+
+    def get_max_velocity(self):
+        v = self.solver.get_max_velocity()
+        return v if self.world == 1 else reduce_max_velocity(self.dist, v, self._device)
+
+    def get_moments_numpy(self):
+        return self.solver.get_moments_numpy()
+
+    def get_physical_fields(self):
+        return self.solver.get_physical_fields()
+
+    # ---- on-device export reduction: ROI / target are global, every rank holds a column range of the frame ----
+    def export_configure(self, x0, x1, y0, y1, target_w, target_h):
+        self.solver.export_configure(x0, x1, y0, y1, target_w, target_h)
+        self.export_columns = self.solver.export_columns
+
+    def export_frame(self, want_frame=True):
+        return self.solver.export_frame(want_frame)
+
+    def export_stats(self):
+        return self.solver.export_stats()
+
+    def gather_columns(self, local):
+        """Concatenate per-rank arrays along their LAST axis (output columns) on rank 0 (None elsewhere)."""
+        if self.world == 1:
+            return local
+        parts = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(local, parts, dst=0)
+        return np.concatenate(parts, axis=-1) if self.rank == 0 else None
+
+    def gather(self, local):
+        """Concatenate per-rank owned-column arrays along x on rank 0 (None elsewhere)."""
+        if self.world == 1:
+            return local
+        parts = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(local, parts, dst=0)
+        return np.concatenate(parts, axis=0) if self.rank == 0 else None
+
+    def synchronize(self):
+        self.solver.synchronize()
+
+    def step_count(self):
+        return self.solver.step_count()
+
+    def launch_count(self):
+        return self.solver.launch_count()
+
+    def device_view(self):
+        return self.solver.device_view()
+
+    def close(self):
+        self.solver.close()

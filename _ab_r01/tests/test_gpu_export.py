@@ -1,0 +1,81 @@
+"""GPU: on-device export reduction (ROI crop + INTER_AREA + running statistics) against the writer oracle
+fed with the CPU oracle's moments, and against cv2 directly."""
+import importlib
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from helpers import cylinder_mask, make_config, random_blocks_mask, rel_linf
+from oracle.lbm_oracle_c import OracleLBMC
+from oracle.writer_oracle import WriterOracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return importlib.import_module("01-lbm-2d_b200")
+
+
+CASES = [  # (nx, ny, sponge, buffer, save_h): general path, integer fast path (3x3 and 2x2), identity
+    (200, 96, (8, 30, 6, 6), 4, 24),
+    (142, 70, (6, 16, 3, 3), 2, 20),
+    (154, 60, (10, 20, 6, 6), 0, 16),
+    (150, 44, (10, 20, 6, 6), 0, 16),
+    (90, 40, (5, 9, 4, 4), 1, 30),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}x{c[1]}_h{c[4]}")
+def test_export_frames_and_stats_bit_exact_in_strict_mode(pkg, case, tmp_path):
+    nx, ny, sponge, buffer, save_h = case
+    cfg = make_config(nx, ny, rho_in=1.02, nu=0.02, warmup=20, sponge=sponge, buffer=buffer, save_h=save_h, compute_step_size=15)
+    mask = cylinder_mask(nx, ny, nx // 3, ny // 2, max(3, ny // 10)) | random_blocks_mask(nx, ny, 4, seed=nx, keep_in=nx // 4, keep_out=nx // 3)
+    ref = OracleLBMC(cfg, mask)
+    ref.init()
+    s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="strict")
+    s.init()
+    dw = importlib.import_module("01-lbm-2d_b200.device_writer")
+    w = dw.DeviceLBMCaseWriter(str(tmp_path / "case.h5"), cfg, nx, ny, mask_data=mask, solver=s)
+    wo = WriterOracle(cfg, nx, ny)
+    assert (w.target_w, w.target_h) == (wo.target_w, wo.target_h)
+    for _ in range(4):
+        ref.run_step(15), s.run_step(15)
+        wo.append(ref.get_moments_numpy())
+        w.append_from_solver(s)
+        m = ref.get_moments_numpy()[wo.slice_x, wo.slice_y, 3].T  # cv2 itself on one channel
+        assert np.array_equal(w.frames[-1][3], cv2.resize(np.ascontiguousarray(m), (w.target_w, w.target_h), interpolation=cv2.INTER_AREA))
+    got, want = w.finalize(), wo.finalize()
+    for k in ("turbulence", "mean_vel_field", "mean_vel_sq_field", "sum_vor"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("stats_min", "stats_max", "stats_mean"):
+        assert np.array_equal(np.asarray(w.attrs[k]), want[k]), k
+    assert got["static_mask"].shape == (2, w.target_h, w.target_w)
+    assert os.path.exists(str(tmp_path / "case.h5")) or os.path.exists(str(tmp_path / "case.npz"))
+
+
+def test_export_fast_arithmetic_within_tolerance_and_run_loop_uses_it(pkg, tmp_path):
+    nx, ny = 256, 96
+    cfg = make_config(nx, ny, rho_in=1.01, nu=0.01, warmup=50, sponge=(8, 24, 4, 4), buffer=4, save_h=22, compute_step_size=20)
+    cfg["outputs"]["start_record_step"] = 40
+    mask = cylinder_mask(nx, ny, 64, 48, 8)
+    ref = OracleLBMC(cfg, mask)
+    ref.init()
+    wo = WriterOracle(cfg, nx, ny)
+    for step in range(20, 101, 20):
+        ref.run_step(20)
+        if step >= 40:
+            wo.append(ref.get_moments_numpy())
+    s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask)
+    s.init()
+    dw = importlib.import_module("01-lbm-2d_b200.device_writer")
+    ops = importlib.import_module("01-lbm-2d_b200.simulation_ops")
+    w = dw.DeviceLBMCaseWriter(str(tmp_path / "c.h5"), cfg, nx, ny, mask_data=mask, solver=s)
+    meta = ops.run_simulation_loop(cfg, s, None, None, None, w, max_steps=100, progress=False)
+    assert meta["status"] == "Success" and len(w.frames) == 4
+    got, want = w.finalize(), wo.finalize()
+    assert rel_linf(got["turbulence"], want["turbulence"]) <= 1e-5
+    assert rel_linf(got["mean_vel_field"], want["mean_vel_field"]) <= 1e-5
+    assert np.abs(got["mean_vel_sq_field"] - want["mean_vel_sq_field"]).max() <= 1e-6

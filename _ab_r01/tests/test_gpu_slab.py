@@ -1,0 +1,33 @@
+"""Multi-GPU x-slab path: N ranks exchanging one halo column per step over NCCL must equal the monolithic
+oracle (bit-exact in strict arithmetic).  Needs >= 2 GPUs; skipped on a single-GPU box (the decomposition logic
+itself is covered on CPU by tests/test_slab_cpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("kernel", ["auto", "tma"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_slabs_over_nccl_equal_monolithic_oracle(world, kernel):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world * 7 + (1 if kernel == "tma" else 0)),
+           os.path.join(ROOT, "tests", "slab_worker.py"), kernel]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("SLAB-OK") == 2, res.stdout[-2000:]

@@ -166,6 +166,20 @@ int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw
 int lbm_comm_unique_id(uint8_t out[LBM_COMM_ID_BYTES]);
 int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id[LBM_COMM_ID_BYTES]);
 
+/* Peer-memory halo path (preferred on NVLink / NVSwitch nodes): after lbm_comm_connect(), every rank exports CUDA IPC
+ * handles of its two population buffers and its inbox counters (lbm_peer_export), the host exchanges the blobs
+ * (torch.distributed all_gather) and each rank maps its neighbours' buffers (lbm_peer_connect; NULL on a side that is a
+ * domain boundary).  From then on a slab step is ONE kernel launch: the CTAs of the first / last owned column store the
+ * populations that cross the interface straight into the neighbour's halo column over NVLink and publish a per-step
+ * counter; the neighbour's edge CTAs of the next step wait on it (bounded; a timeout surfaces as LBM_ERR_NCCL from the
+ * next getter).  No NCCL call is left on the per-step path, and programmatic dependent launch + early start work as on
+ * one GPU.  If lbm_peer_connect() fails (no peer access) the handle keeps the NCCL exchange above.  All ranks must
+ * call lbm_init() and reach a host barrier before any of them steps (slab.py does), and must not destroy a handle while a
+ * neighbour may still be stepping. */
+#define LBM_PEER_HANDLE_BYTES 256
+int lbm_peer_export(LbmHandle h, uint8_t out[LBM_PEER_HANDLE_BYTES]);
+int lbm_peer_connect(LbmHandle h, const uint8_t *west_blob, const uint8_t *east_blob);
+
 /* ---- HBM-resident access (no host copies): device pointers valid until lbm_destroy ---------- */
 typedef struct {
     float *f_cur;      /* 9 planes, plane stride `plane_stride` floats, (nx_local, pitch) y fastest */
@@ -180,6 +194,14 @@ int lbm_device_view(LbmHandle h, LbmDeviceView *out);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int lbm_launch_count(LbmHandle h, int64_t *launches);
+
+/* Page-locked host memory for the large device -> host getters.  The reference hands out a FRESH (nx, ny, 9) numpy array
+ * per export (ref:739-741; it is queued to the writer thread, io/lbm_writer.py:260-287), which as a pageable allocation
+ * costs first-touch page faults plus a staged copy -- 3.5 GB/s instead of PCIe speed.  The Python binding therefore keeps
+ * a small pool of these buffers and wraps one per call in a caller-owned array that returns it to the pool when it is
+ * garbage collected; every getter DMAs straight into a destination allocated here. */
+int lbm_host_alloc(size_t bytes, void **out);
+int lbm_host_free(void *ptr);
 
 /* Self test of the strict kernel's inline packed division / square root (two cells per FFMA2 pair) against CUDA's
  * correctly rounded __fdiv_rn / __fsqrt_rn on `pairs` random operand pairs from the range the kernel admits to the

@@ -46,7 +46,7 @@ def test_export_frames_and_stats_bit_exact_in_strict_mode(pkg, case, tmp_path):
         wo.append(ref.get_moments_numpy())
         w.append_from_solver(s)
         m = ref.get_moments_numpy()[wo.slice_x, wo.slice_y, 3].T  # cv2 itself on one channel
-        assert np.array_equal(w.frames[-1][3], cv2.resize(np.ascontiguousarray(m), (w.target_w, w.target_h), interpolation=cv2.INTER_AREA))
+        assert np.array_equal(w.last_frame[3], cv2.resize(np.ascontiguousarray(m), (w.target_w, w.target_h), interpolation=cv2.INTER_AREA))
     got, want = w.finalize(), wo.finalize()
     for k in ("turbulence", "mean_vel_field", "mean_vel_sq_field", "sum_vor"):
         assert np.array_equal(got[k], want[k]), k
@@ -68,13 +68,13 @@ def test_export_fast_arithmetic_within_tolerance_and_run_loop_uses_it(pkg, tmp_p
         ref.run_step(20)
         if step >= 40:
             wo.append(ref.get_moments_numpy())
-    s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask)
+    s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="fast")
     s.init()
     dw = importlib.import_module("01-lbm-2d_b200.device_writer")
     ops = importlib.import_module("01-lbm-2d_b200.simulation_ops")
     w = dw.DeviceLBMCaseWriter(str(tmp_path / "c.h5"), cfg, nx, ny, mask_data=mask, solver=s)
     meta = ops.run_simulation_loop(cfg, s, None, None, None, w, max_steps=100, progress=False)
-    assert meta["status"] == "Success" and len(w.frames) == 4
+    assert meta["status"] == "Success" and w.n_frames == 4
     got, want = w.finalize(), wo.finalize()
     assert rel_linf(got["turbulence"], want["turbulence"]) <= 1e-5
     assert rel_linf(got["mean_vel_field"], want["mean_vel_field"]) <= 1e-5

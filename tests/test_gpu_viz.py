@@ -23,9 +23,9 @@ def test_fields_bit_identical_to_scipy_and_numpy(pkg, nx, ny):
     mask = cylinder_mask(nx, ny, nx // 4, ny // 2, max(1, min(nx, ny) // 8)) if min(nx, ny) > 8 else None
     s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask)
     s.init()
-    s.run_step(200)
+    s.run_step(200 if nx > 8 else 40)   # the 3-column channel accelerates without bound (it blows up in the oracle too)
     vel = s.vel.to_numpy()
-    assert np.abs(vel).max() > 1e-4
+    assert np.isfinite(vel).all() and np.abs(vel).max() > 1e-4
     for sigma in (1.0, 2.5, 0.6, 0.0):     # radius 4, 10 (longer than the short grids: repeated reflection), 2, off
         mag, vor = s.get_viz_fields(sigma)
         want_mag, want_vor = viz_oracle.viz_fields(vel, sigma)
