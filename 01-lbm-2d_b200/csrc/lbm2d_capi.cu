@@ -506,9 +506,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     if (p.warmup_steps < 0) return fail(LBM_ERR_INVALID, "warmup_steps < 0");
     if (p.obstacle_mode != LBM_OBSTACLE_REFILL && p.obstacle_mode != LBM_OBSTACLE_BOUNCE_BACK)
         return fail(LBM_ERR_INVALID, "unsupported obstacle_mode");
-    if (p.obstacle_mode == LBM_OBSTACLE_BOUNCE_BACK &&
-        ((p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER) || (p.nx_global > 0 && p.nx_global != p.nx)))
-        return fail(LBM_ERR_INVALID, "obstacle_mode bounce-back: single GPU and the default kernel only");
+    if (p.obstacle_mode == LBM_OBSTACLE_BOUNCE_BACK && p.kernel != LBM_KERNEL_AUTO && p.kernel != LBM_KERNEL_REGISTER)
+        return fail(LBM_ERR_INVALID, "obstacle_mode bounce-back: the default (register) kernel only");
     if (p.arith != LBM_ARITH_FAST && p.arith != LBM_ARITH_STRICT) return fail(LBM_ERR_INVALID, "unsupported arith");
     if (p.warmup_steps > (1 << 26)) return fail(LBM_ERR_INVALID, "warmup_steps too large for the ramp table");
 
@@ -792,7 +791,7 @@ int lbm_peer_connect(LbmHandle h, const uint8_t *west, const uint8_t *east) {
     if (int rc = check_handle(h, false)) return rc;
     if ((west != nullptr) == h->west_ring || (east != nullptr) == h->east_ring)
         return fail(LBM_ERR_INVALID, "a neighbour blob is needed exactly on the sides that are halos");
-    if (h->use_tma || h->links8) return fail(LBM_ERR_INVALID, "peer-memory halos: register kernel, refill obstacle mode");
+    if (h->use_tma) return fail(LBM_ERR_INVALID, "peer-memory halos: register kernel only");
     const uint8_t *blobs[2] = {west, east};
     for (int side = 0; side < 2; ++side) {
         if (!blobs[side]) continue;
@@ -920,7 +919,7 @@ int lbm_run(LbmHandle h, int steps) {
             if (emit) CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));  // orders the max|u| reset before the edge kernel
             CUDA_TRY(cudaStreamWaitEvent(h->stream_e, h->ev_m, 0));
             const dim3 eb = grid_for(e);
-            CUDA_TRY(launch_step(step_fn(strict, emit, false), eb, h->stream_e, e, false));
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr), eb, h->stream_e, e, false));
             CUDA_TRY(cudaEventRecord(h->ev_e, h->stream_e));
             if (int rc = exchange_halos(h, a.dst, h->stream_e)) return rc;
             h->launches++;
@@ -1068,23 +1067,61 @@ int lbm_get_viz_fields(LbmHandle h, const double *weights, int radius, float *ou
     if (int rc = check_handle(h, true)) return rc;
     if (!out_mag || !out_vor) return fail(LBM_ERR_INVALID, "out is null");
     if (radius < 0 || radius > 4096 || (radius > 0 && !weights)) return fail(LBM_ERR_INVALID, "bad filter radius / weights");
-    if (!(h->west_ring && h->east_ring)) return fail(LBM_ERR_INVALID, "viz fields: single GPU only (the filter reaches across slab borders)");
-    const int nx = h->p.nx, ny = h->ny;
-    const size_t n = (size_t)nx * ny, wfloats = 2 * ((size_t)radius + 2);   // the weights ride in front (8-byte aligned)
-    if (int rc = ensure_staging(h, wfloats + 6 * n)) return rc;
+    const bool slabs = h->comm && h->nranks > 1;
+    if (!slabs && !(h->west_ring && h->east_ring)) return fail(LBM_ERR_STATE, "viz fields on a slab handle need lbm_comm_connect() first");
+    const int nx = h->p.nx, ny = h->ny, NX = h->p.nx_global, x0 = h->p.slab_x0;
+    // x-slabs: the x pass of the filter reaches `radius` columns into the neighbours and the vorticity one column
+    // further, so radius + 1 raw velocity columns come from each neighbour (NCCL, contiguous: y is the fast index);
+    // reflection and the one-sided differences happen at the GLOBAL edges, so the owned columns are bit-identical to
+    // the single-GPU result.
+    const int hw = h->west_ring ? 0 : radius + 1, he = h->east_ring ? 0 : radius + 1;   // raw halo columns
+    const int ew = h->west_ring ? 0 : 1, ee = h->east_ring ? 0 : 1;                     // filtered halo columns
+    if (slabs && radius + 1 > nx) return fail(LBM_ERR_INVALID, "viz fields: the filter radius exceeds the slab width");
+    const int nxe = hw + nx + he, nxo = ew + nx + ee;
+    const size_t n = (size_t)nx * ny, no = (size_t)nxo * ny, wfloats = 2 * ((size_t)radius + 2);   // the weights ride in front (8-byte aligned)
+    const size_t ext = (size_t)nxe * h->pitch;
+    if (int rc = ensure_staging(h, wfloats + 2 * ext + 4 * no + 2 * n)) return rc;
     double *w = reinterpret_cast<double *>(h->staging);
-    float *t0 = h->staging + wfloats, *t1 = t0 + n, *v0 = t1 + n, *v1 = v0 + n, *mag = v1 + n, *vor = mag + n;
-    const dim3 grid(nx, (ny + 127) / 128);
-    const float *vx = h->ux, *vy = h->uy;
+    float *e0 = h->staging + wfloats, *e1 = e0 + ext, *t0 = e1 + ext, *t1 = t0 + no, *v0 = t1 + no, *v1 = v0 + no, *mag = v1 + no, *vor = mag + n;
+    // raw velocity with neighbour columns: row 0 = global column x0 - hw, pitched like the planes
+    const float *rx = h->ux + (size_t)h->own0 * h->pitch, *ry = h->uy + (size_t)h->own0 * h->pitch;
+    int gin0 = x0;
+    if (slabs) {
+        const size_t own = (size_t)nx * h->pitch;
+        CUDA_TRY(cudaMemcpyAsync(e0 + (size_t)hw * h->pitch, rx, own * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(e1 + (size_t)hw * h->pitch, ry, own * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        nccl::Api &nc = nccl::api();
+        const size_t cnt = (size_t)(radius + 1) * h->pitch;
+        NCCL_TRY(nc.GroupStart());
+        if (!h->west_ring) {
+            NCCL_TRY(nc.Send(rx, cnt, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+            NCCL_TRY(nc.Send(ry, cnt, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+            NCCL_TRY(nc.Recv(e0, cnt, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+            NCCL_TRY(nc.Recv(e1, cnt, nccl::kFloat32, h->rank - 1, h->comm, h->stream));
+        }
+        if (!h->east_ring) {
+            NCCL_TRY(nc.Send(rx + own - cnt, cnt, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+            NCCL_TRY(nc.Send(ry + own - cnt, cnt, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+            NCCL_TRY(nc.Recv(e0 + (size_t)(hw + nx) * h->pitch, cnt, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+            NCCL_TRY(nc.Recv(e1 + (size_t)(hw + nx) * h->pitch, cnt, nccl::kFloat32, h->rank + 1, h->comm, h->stream));
+        }
+        NCCL_TRY(nc.GroupEnd());
+        rx = e0;
+        ry = e1;
+        gin0 = x0 - hw;
+    }
+    const dim3 grid(nx, (ny + 127) / 128), grid_o(nxo, (ny + 127) / 128);
+    const float *vx = rx, *vy = ry;
     long long sx = h->pitch;
+    int gv0 = gin0;   // global column of row 0 of (vx, vy)
     if (radius > 0) {
         CUDA_TRY(cudaMemcpyAsync(w, weights, ((size_t)radius + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        lbm::viz_blur_kernel<<<grid, 128, 0, h->stream>>>(h->ux, h->uy, h->pitch, nx, ny, 0, radius, w, t0, t1);
-        lbm::viz_blur_kernel<<<grid, 128, 0, h->stream>>>(t0, t1, ny, nx, ny, 1, radius, w, v0, v1);
-        vx = v0; vy = v1; sx = ny;
+        lbm::viz_blur_kernel<<<grid_o, 128, 0, h->stream>>>(rx, ry, h->pitch, nxo, ny, 0, radius, w, t0, t1, x0 - ew, gin0, NX);
+        lbm::viz_blur_kernel<<<grid_o, 128, 0, h->stream>>>(t0, t1, ny, nxo, ny, 1, radius, w, v0, v1, 0, 0, NX);
+        vx = v0; vy = v1; sx = ny; gv0 = x0 - ew;
         h->launches += 2;
     }
-    lbm::viz_fields_kernel<<<grid, 128, 0, h->stream>>>(vx, vy, sx, nx, ny, mag, vor);
+    lbm::viz_fields_kernel<<<grid, 128, 0, h->stream>>>(vx, vy, sx, nx, ny, mag, vor, x0, gv0, NX);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (int rc = d2h(h, out_mag, mag, n * sizeof(float))) return rc;

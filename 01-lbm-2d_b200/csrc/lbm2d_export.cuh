@@ -189,14 +189,16 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
 // One pass of NI_Correlate1D (symmetric kernel): centre tap first, then the pairs from the outermost inwards,
 // (in[-j] + in[+j]) * w[j], accumulated in double with every operation rounded on its own; float32 out.
 // in: element (x, y) at x * sx + y; out: (nx, ny) unpitched.  axis 0 = along x, 1 = along y.  Two fields at once.
+// x-slabs: row x of the OUTPUT is global column gout0 + x, row q of the INPUT is global column gin0 + q, and the
+// reflection along x happens at the GLOBAL edges [0, nx_global) -- the input carries enough neighbour columns.
 __global__ void viz_blur_kernel(const float *__restrict__ in0, const float *__restrict__ in1, long long sx, int nx, int ny,
                                 int axis, int radius, const double *__restrict__ w, float *__restrict__ out0,
-                                float *__restrict__ out1) {
+                                float *__restrict__ out1, int gout0, int gin0, int nx_global) {
     const int y = blockIdx.y * blockDim.x + threadIdx.x, x = blockIdx.x;
     if (y >= ny) return;
-    const int pos = axis == 0 ? x : y, n = axis == 0 ? nx : ny;
+    const int pos = axis == 0 ? gout0 + x : y, n = axis == 0 ? nx_global : ny;
     auto at = [&](const float *in, int q) {
-        return (double)(axis == 0 ? in[(long long)q * sx + y] : in[(long long)x * sx + q]);
+        return (double)(axis == 0 ? in[(long long)(q - gin0) * sx + y] : in[(long long)x * sx + q]);
     };
     double a0 = __dmul_rn(at(in0, pos), w[0]), a1 = __dmul_rn(at(in1, pos), w[0]);
     for (int j = radius; j > 0; --j) {
@@ -210,20 +212,22 @@ __global__ void viz_blur_kernel(const float *__restrict__ in0, const float *__re
 }
 
 // vel_mag = sqrt(vx^2 + vy^2); vor = np.gradient(vx)[1] - np.gradient(vy)[0] (float32: central differences / 2 inside,
-// one-sided at the edges).  vx, vy: element (x, y) at x * sx + y.
+// one-sided at the edges).  vx, vy: element (x, y) at x * sx + y, row 0 = global column gin0; output row x = global
+// column gout0 + x (x-slabs: the input holds one neighbour column on every side that is not a global edge).
 __global__ void viz_fields_kernel(const float *__restrict__ vx, const float *__restrict__ vy, long long sx, int nx, int ny,
-                                  float *__restrict__ mag, float *__restrict__ vor) {
+                                  float *__restrict__ mag, float *__restrict__ vor, int gout0, int gin0, int nx_global) {
     const int y = blockIdx.y * blockDim.x + threadIdx.x, x = blockIdx.x;
     if (y >= ny) return;
-    auto U = [&](int xx, int yy) { return vx[(long long)xx * sx + yy]; };
-    auto Vv = [&](int xx, int yy) { return vy[(long long)xx * sx + yy]; };
-    const float u = U(x, y), v = Vv(x, y);
-    const float dudy = (y == 0)        ? __fsub_rn(U(x, 1), U(x, 0))
-                       : (y == ny - 1) ? __fsub_rn(U(x, ny - 1), U(x, ny - 2))
-                                       : __fdiv_rn(__fsub_rn(U(x, y + 1), U(x, y - 1)), 2.0f);
-    const float dvdx = (x == 0)        ? __fsub_rn(Vv(1, y), Vv(0, y))
-                       : (x == nx - 1) ? __fsub_rn(Vv(nx - 1, y), Vv(nx - 2, y))
-                                       : __fdiv_rn(__fsub_rn(Vv(x + 1, y), Vv(x - 1, y)), 2.0f);
+    const int g = gout0 + x;
+    auto U = [&](int gg, int yy) { return vx[(long long)(gg - gin0) * sx + yy]; };
+    auto Vv = [&](int gg, int yy) { return vy[(long long)(gg - gin0) * sx + yy]; };
+    const float u = U(g, y), v = Vv(g, y);
+    const float dudy = (y == 0)        ? __fsub_rn(U(g, 1), U(g, 0))
+                       : (y == ny - 1) ? __fsub_rn(U(g, ny - 1), U(g, ny - 2))
+                                       : __fdiv_rn(__fsub_rn(U(g, y + 1), U(g, y - 1)), 2.0f);
+    const float dvdx = (g == 0)               ? __fsub_rn(Vv(1, y), Vv(0, y))
+                       : (g == nx_global - 1) ? __fsub_rn(Vv(nx_global - 1, y), Vv(nx_global - 2, y))
+                                              : __fdiv_rn(__fsub_rn(Vv(g + 1, y), Vv(g - 1, y)), 2.0f);
     const long long o = (long long)x * ny + y;
     mag[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
     vor[o] = __fsub_rn(dudy, dvdx);

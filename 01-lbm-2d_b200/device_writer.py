@@ -9,8 +9,9 @@ where the work happens: `append_from_solver(solver)` asks the solver for the alr
 export at 8192x2048, and the running sums live on the device until `finalize()`.
 
 Like the reference, the file is opened in the constructor and every frame is appended to the resizable, chunked
-`turbulence` dataset as it arrives (writer:69, 112-119, 167-169): host memory stays at ONE frame however long the
-case runs, and a killed run leaves its frames on disk.
+`turbulence` dataset as it arrives (writer:69, 112-119, 167-169), by a worker thread behind a queue of depth 5 (the
+reference's AsyncLBMCaseWriter, writer:260-296): host memory stays bounded however long the case runs, a killed run
+leaves its frames on disk, and file I/O overlaps the next batch of steps.
 
 Container.  HDF5 through h5py, as in the reference (`container="h5"`).  h5py is absent from the build image, so
 there is a second, explicitly named container for such hosts: `container="raw"` streams the frames to
@@ -22,7 +23,9 @@ from __future__ import annotations
 
 import json
 import os
+import queue
 import sys
+import threading
 
 import numpy as np
 
@@ -116,6 +119,41 @@ def static_mask_host(mask, x0, x1, y0, y1, target_w, target_h):
     return np.stack([small, sdf], axis=0).astype(np.float32)
 
 
+class _AsyncAppender:
+    """File writes off the solver thread, as the reference's AsyncLBMCaseWriter does (writer:260-296): a bounded
+    queue (depth 5) feeds one worker thread that appends to the container; `drain()` joins it."""
+
+    def __init__(self, container, depth=5):
+        self.container, self.error = container, None
+        self.queue = queue.Queue(maxsize=depth)
+        self.thread = threading.Thread(target=self._worker, name="lbm-case-writer", daemon=True)
+        self.thread.start()
+
+    def _worker(self):
+        while True:
+            frame = self.queue.get()
+            try:
+                if frame is None:
+                    return
+                self.container.append(frame)
+            except Exception as e:  # surfaced by drain()
+                self.error = e
+            finally:
+                self.queue.task_done()
+
+    def append(self, frame):
+        self.queue.put(frame)
+
+    def flush(self):
+        self.queue.join()
+
+    def drain(self):
+        self.queue.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
 class DeviceLBMCaseWriter:
     def __init__(self, file_path, config, nx, ny, channels=9, mask_data=None, solver=None, container="auto"):
         os.makedirs(os.path.dirname(os.path.abspath(file_path)), exist_ok=True)
@@ -178,6 +216,7 @@ class DeviceLBMCaseWriter:
         if self._is_writer_rank():
             cls = _H5Container if self._container_kind == "h5" else _RawContainer
             self._container = cls(self.file_path, self.channels, self.target_h, self.target_w, self.compression, self.static_mask)
+            self._appender = _AsyncAppender(self._container)
 
     def attach(self, solver):
         solver.export_configure(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
@@ -194,9 +233,14 @@ class DeviceLBMCaseWriter:
         if getattr(sv, "world", 1) > 1:   # x-slabs: every rank holds a column range of the frame; rank 0 writes
             frame = sv.gather_columns(frame)
         if self._container is not None:
-            self._container.append(frame)
+            self._appender.append(frame)   # the frame is a fresh array: the worker thread owns it from here
         self.last_frame = frame
         self.n_frames += 1
+
+    def flush(self):
+        """Block until every frame handed over so far is in the file."""
+        if self._container is not None:
+            self._appender.flush()
 
     def append(self, moment_data):
         raise TypeError("DeviceLBMCaseWriter takes frames from the solver: use append_from_solver(solver); "
@@ -209,6 +253,8 @@ class DeviceLBMCaseWriter:
         self.is_closed = True
         sv = self._solver
         st = sv.export_stats() if sv is not None else {"running_count": 0}
+        if self._container is None and getattr(sv, "world", 1) == 1:
+            self._open()
         if getattr(sv, "world", 1) > 1:
             parts = {k: sv.gather_columns(st[k]) for k in ("running_sum", "running_vel_sq_sum", "sum_abs_vor")}
             mins = sv.gather_columns(st["global_min"][:, None])
@@ -229,6 +275,7 @@ class DeviceLBMCaseWriter:
             attrs = {"config_json": json.dumps(meta, default=str), "stats_min": st["global_min"], "stats_max": st["global_max"],
                      "stats_mean": np.mean(mean_field, axis=(1, 2))}
         self.attrs = attrs
+        self._appender.drain()
         self._container.finalize(out, attrs)
         self.result = read_case(self.file_path)
         return self.result

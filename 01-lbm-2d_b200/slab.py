@@ -98,7 +98,7 @@ class SlabLBM:
     (`gather_*` assemble the global array on rank 0)."""
 
     def __init__(self, config, mask_data=None, *, rank, world, device=None, arith="strict", kernel="auto", dist=None,
-                 halo="auto"):
+                 halo="auto", obstacle_mode="refill"):
         if dist is None:
             import torch.distributed as dist
         self.dist, self.rank, self.world = dist, rank, world
@@ -106,7 +106,7 @@ class SlabLBM:
         self.slabs = partition(nx, world)
         self.x0, self.nx_owned = self.slabs[rank]
         self.solver = LBM2D_MRT_LES(config, mask_data, arith=arith, kernel=kernel, device=device,
-                                    slab=(self.x0, self.nx_owned) if world > 1 else None)
+                                    slab=(self.x0, self.nx_owned) if world > 1 else None, obstacle_mode=obstacle_mode)
         self._device = None
         if world > 1:
             import torch
@@ -179,6 +179,11 @@ class SlabLBM:
     def get_physical_fields(self):
         return self.solver.get_physical_fields()
 
+    def get_viz_fields(self, sigma=None):
+        """(|u|, vorticity) of this rank's owned columns; the filter and the gradients reach into the neighbours'
+        columns (exchanged inside the call), so `gather()` of the parts equals the single-GPU fields bit for bit."""
+        return self.solver.get_viz_fields(sigma)
+
     # ---- on-device export reduction: ROI / target are global, every rank holds a column range of the frame ----
     def export_configure(self, x0, x1, y0, y1, target_w, target_h):
         self.solver.export_configure(x0, x1, y0, y1, target_w, target_h)
@@ -214,7 +219,7 @@ class SlabLBM:
         self.dist.gather(pad, parts, dst=0)
         if self.rank != 0:
             return None
-        return np.concatenate([p[..., :w].cpu().numpy() for p, w in zip(parts, widths)], axis=-1)
+        return torch.cat([p[..., :w] for p, w in zip(parts, widths)], dim=-1).cpu().numpy()   # one D2H copy
 
     def gather(self, local):
         """Concatenate per-rank owned-column arrays along x on rank 0 (None elsewhere)."""

@@ -72,7 +72,36 @@ def main():
                     assert rel_linf(fields[nm], want[nm]) <= 1e-5, (arith, nm)
                 assert np.abs(fields["vel"] - ref.vel).max() <= 2e-6
                 assert np.abs(force - F).max() <= 2e-5 * S + 1e-9
-            print(f"SLAB-OK world={world} arith={arith} kernel={kernel} maxv={maxv:.6f} F={force}")
+            print(f"SLAB-OK world={world} arith={arith} kernel={kernel} halo={s.halo_path} maxv={maxv:.6f} F={force}")
+        s.close()
+    # ---- video-frame fields on slabs: filter / gradient reach across the slab borders (strict state from above is gone:
+    # a fresh short run), and the optional bounce-back obstacle mode on slabs against the numpy oracle's rule
+    from oracle import viz_oracle
+    from oracle.lbm_oracle_np import OracleLBM
+
+    if kernel != "tma":
+        s = slab.SlabLBM(cfg, mask, rank=rank, world=world, device=local)
+        s.init()
+        s.run_step(40)
+        vel = s.gather(s.vel.to_numpy())
+        for sigma in (1.0, 2.5, 0.0):
+            mag, vor = s.get_viz_fields(sigma)
+            mag, vor = s.gather(mag), s.gather(vor)
+            if rank == 0:
+                want_mag, want_vor = viz_oracle.viz_fields(vel, sigma)
+                assert np.array_equal(mag, want_mag) and np.array_equal(vor, want_vor), ("viz", sigma)
+        s.close()
+        bcfg = make_config(nx, ny, rho_in=1.02, nu=0.03, warmup=5, sponge=(6, 20, 4, 4))
+        s = slab.SlabLBM(bcfg, mask, rank=rank, world=world, device=local, obstacle_mode="bounce_back")
+        s.init()
+        s.run_step(45)
+        f_old, rho = s.gather(s.solver.f_old.to_numpy()), s.gather(s.rho.to_numpy())
+        if rank == 0:
+            ref = OracleLBM(bcfg, mask, obstacle_mode="bounce_back")
+            ref.init()
+            ref.run_step(45)
+            assert np.array_equal(f_old, ref.f_old) and np.array_equal(rho, ref.rho), "bounce-back on slabs"
+            print(f"SLAB-EXTRAS-OK world={world} halo={s.halo_path}")
         s.close()
     dist.barrier()
     dist.destroy_process_group()

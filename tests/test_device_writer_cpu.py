@@ -51,6 +51,7 @@ def test_frames_are_streamed_and_the_reference_dataset_set_is_written(tmp_path, 
     assert not hasattr(w, "frames")                      # nothing accumulates on the host
     for i in range(5):
         w.append_from_solver()
+        w.flush()                                        # the worker thread has appended it
         if container == "h5":                            # the frame is in the file BEFORE finalize (writer:167-169)
             d = fake_h5py.FILES[str(tmp_path / "case.h5")]["turbulence"]
             assert d.shape[0] == i + 1 and d.maxshape[0] is None and d.chunks == (1, 9, w.target_h, w.target_w)

@@ -39,7 +39,7 @@ def test_strict_build_bit_exact_vs_the_oracle_rule(pkg):
             assert np.array_equal(s.rho.to_numpy(), ref.rho, equal_nan=True), tag
             assert np.array_equal(s.vel.to_numpy(), ref.vel, equal_nan=True), tag
             assert np.array_equal(s.get_moments_numpy(), ref.get_moments_numpy(), equal_nan=True), tag
-        f = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, obstacle_mode="bounce_back")
+        f = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith="fast", obstacle_mode="bounce_back")
         f.init()
         f.run_step(40)
         if np.isfinite(ref.f_old).all():
@@ -84,7 +84,6 @@ def test_mode_is_restricted_to_the_default_kernel(pkg):
     cfg = make_config(32, 16)
     with pytest.raises(capi.LbmError, match="bounce-back"):
         pkg.LBM2D_MRT_LES(cfg, obstacle_mode="bounce_back", kernel="tma")
-    with pytest.raises(capi.LbmError, match="bounce-back"):
-        pkg.LBM2D_MRT_LES(cfg, obstacle_mode="bounce_back", slab=(0, 16))
+    pkg.LBM2D_MRT_LES(cfg, obstacle_mode="bounce_back", slab=(0, 16)).close()   # slabs are fine (tests/slab_worker.py)
     with pytest.raises(KeyError):
         pkg.LBM2D_MRT_LES(cfg, obstacle_mode="on_node")

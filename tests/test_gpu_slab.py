@@ -31,3 +31,17 @@ def test_slabs_over_nccl_equal_monolithic_oracle(world, kernel):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("SLAB-OK") == 2, res.stdout[-2000:]
+    if kernel == "auto":   # the register kernel takes the peer-memory halo path on NVLink boxes; extras: viz fields, bounce-back
+        assert "halo=peer" in res.stdout and "SLAB-EXTRAS-OK" in res.stdout, res.stdout[-2000:]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_slabs_over_nccl_fallback_path(world):
+    """The grouped ncclSend/ncclRecv exchange stays as the fallback of the peer-memory path: force it."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "slab_worker.py"), "auto"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, LBM2D_HALO="nccl"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("SLAB-OK") == 2 and "halo=nccl" in res.stdout and "SLAB-EXTRAS-OK" in res.stdout
