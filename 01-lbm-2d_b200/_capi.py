@@ -63,6 +63,8 @@ EXPORTS = {
     "lbm_export_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "lbm_static_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.POINTER(C.c_int32)]),
     "lbm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lbm_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),

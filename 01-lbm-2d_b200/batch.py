@@ -201,17 +201,14 @@ def run_cases(cases, out_dir, rank=0, world=1, device=None, max_steps=None, prog
     return results
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--sweep", type=int, default=64, help="number of synthetic 1024x256 cases (seeds 0..N-1)")
-    ap.add_argument("--out", default="gpurun_out/sweep")
-    ap.add_argument("--max-steps", type=int, default=None)
-    ap.add_argument("--max-success", type=int, default=None)
-    ap.add_argument("--no-resume", action="store_true")
-    ap.add_argument("--concurrency", type=int, default=1, help="cases in flight per GPU (threads, one stream each)")
-    args = ap.parse_args()
+def run_sweep(n_cases=64, out_dir="gpurun_out/sweep", max_steps=None, max_success=None, resume=False, concurrency=2,
+              emit=print):
+    """BASELINE configs[4]: `n_cases` procedural 1024x256 cases (seeds 0 .. n-1), one process per GPU (torchrun), every
+    case through the run loop with the device-side writer.  Rank 0 emits ONE JSON line: cases/hour over all ranks,
+    process start-up (CUDA context, imports) excluded and reported.  Also what `bench.py --workload sweep` runs."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, root)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from benchmarks import workloads as W
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,8 +219,9 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cases = {f"sweep_{s:02d}": W.sweep_case(s) for s in range(args.sweep)}
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cases = {f"sweep_{s:02d}": W.sweep_case(s) for s in range(n_cases)}
     # process start-up (CUDA context, module load, cv2 / scipy imports) is paid once per worker, not per case:
     # keep it out of the cases/hour window and report it separately
     t_start = time.perf_counter()
@@ -236,26 +234,54 @@ def main():
     warm.get_max_velocity()
     warm.close()
     startup_s = time.perf_counter() - t_start
-    if rank == 0 and world > 1:
-        consolidate(args.out)
+    if rank == 0:
+        if not resume:   # a benchmark run starts from nothing
+            import shutil
+
+            shutil.rmtree(out_dir, ignore_errors=True)
+        elif world > 1:
+            consolidate(out_dir)
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    run_cases(cases, args.out, rank, world, device=local, max_steps=args.max_steps,
-              resume=not args.no_resume, max_success=args.max_success, concurrency=args.concurrency)
+    run_cases(cases, out_dir, rank, world, device=local, max_steps=max_steps, resume=resume, max_success=max_success,
+              concurrency=concurrency)
     if dist is not None:
         dist.barrier()
     dt = time.perf_counter() - t0
+    line = None
     if rank == 0:
-        before = load_status_map(args.out)
-        merged = merge_shards(args.out, world, remove=True)
+        before = load_status_map(out_dir)
+        merged = merge_shards(out_dir, world, remove=True)
         ran_now = [n for n in merged if before.get(n) not in ("Success", "Failed")]   # skipped cases cost no time
         ok = sum(1 for r in merged.values() if r["status"] == "Success")
         steps = sum(merged[n].get("final_steps", 0) for n in ran_now)
-        print(json.dumps({"metric": "cases/hour (64 x 1024x256 sweep incl. export)", "value": len(ran_now) / dt * 3600,
-                          "n_gpus": world, "concurrency": args.concurrency, "cases": len(ran_now), "cases_recorded": len(merged), "success": ok,
-                          "total_steps": steps, "wall_s": dt, "startup_s_excluded": startup_s}))
-    if dist is not None:
+        cfg0 = first[0]
+        line = {"metric": "cases/hour (procedural 1024x256 sweep incl. export, BASELINE configs[4])", "value": len(ran_now) / dt * 3600,
+                "unit": "cases/hour", "n_gpus": world, "higher_is_better": True, "scaling": "weak" if n_cases % max(world, 1) == 0 else "strong",
+                "dtype": "f32", "data": "synthetic", "concurrency": concurrency, "cases": len(ran_now), "cases_recorded": len(merged),
+                "success": ok, "total_steps": steps, "steps_per_case": steps // max(1, len(ran_now)), "wall_s": dt,
+                "startup_s_excluded": startup_s, "mlups_aggregate": steps * cfg0["simulation"]["nx"] * cfg0["simulation"]["ny"] / dt / 1e6,
+                "config": {"workload": f"{n_cases} procedural masks 1024x256 (circles / rotated squares / triangles), replica mode: one "
+                                       f"process per GPU, {concurrency} cases in flight per GPU, run loop + device-side writer + file output",
+                           "arith": "strict"}}
+        emit(json.dumps(line))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", type=int, default=64, help="number of synthetic 1024x256 cases (seeds 0..N-1)")
+    ap.add_argument("--out", default="gpurun_out/sweep")
+    ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--max-success", type=int, default=None)
+    ap.add_argument("--no-resume", action="store_true")
+    ap.add_argument("--concurrency", type=int, default=1, help="cases in flight per GPU (threads, one stream each)")
+    args = ap.parse_args()
+    run_sweep(args.sweep, args.out, args.max_steps, args.max_success, not args.no_resume, args.concurrency)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 

@@ -1333,6 +1333,55 @@ int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw
     return LBM_OK;
 }
 
+int lbm_static_mask(LbmHandle h, int32_t x0, int32_t x1, int32_t y0, int32_t y1, int32_t tw, int32_t th, float *out,
+                    int32_t *degenerate) {
+    if (int rc = check_handle(h, false)) return rc;
+    if (!out || !degenerate) return fail(LBM_ERR_INVALID, "out / degenerate is null");
+    if (h->p.nx != h->p.nx_global) return fail(LBM_ERR_INVALID, "static mask: single GPU only (the mask of a slab is partial)");
+    const int cw = x1 - x0, ch = y1 - y0;
+    if (x0 < 0 || y0 < 0 || x1 > h->p.nx || y1 > h->ny || cw <= 0 || ch <= 0 || tw < 1 || th < 1)
+        return fail(LBM_ERR_INVALID, "static mask: ROI outside the grid or empty target");
+    // cv::resize INTER_NEAREST (resizeNN): x_ofs[x] = min(cvFloor(x * ifx), ssize.width - 1), ifx = 1 / (dsize / ssize)
+    std::vector<int> xs(tw), ys(th);
+    const double ifx = 1.0 / ((double)tw / (double)cw), ify = 1.0 / ((double)th / (double)ch);
+    for (int x = 0; x < tw; ++x) xs[x] = x0 + std::min((int)std::floor(x * ifx), cw - 1);
+    for (int y = 0; y < th; ++y) ys[y] = y0 + std::min((int)std::floor(y * ify), ch - 1);
+    const size_t n = (size_t)tw * th;
+    // scratch layout (bytes): xs | ys | counts | small | g | d_fluid | d_solid | out
+    const size_t off_ys = (size_t)tw * 4, off_cnt = off_ys + (size_t)th * 4, off_small = (off_cnt + 4 + 15) / 16 * 16;
+    const size_t off_g = (off_small + n + 15) / 16 * 16, off_df = (off_g + n * 4 + 15) / 16 * 16, off_ds = off_df + n * 8;
+    const size_t off_out = off_ds + n * 8, total = off_out + 2 * n * 4;
+    if (int rc = ensure_staging(h, (total + 3) / 4)) return rc;
+    char *base = reinterpret_cast<char *>(h->staging);
+    int *d_xs = (int *)base, *d_ys = (int *)(base + off_ys), *d_cnt = (int *)(base + off_cnt), *d_g = (int *)(base + off_g);
+    uint8_t *d_small = (uint8_t *)(base + off_small);
+    double *d_df = (double *)(base + off_df), *d_ds = (double *)(base + off_ds);
+    float *d_out = (float *)(base + off_out);
+    CUDA_TRY(cudaMemcpyAsync(d_xs, xs.data(), (size_t)tw * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ys, ys.data(), (size_t)th * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, h->stream));
+    const dim3 grid2((tw + 127) / 128, th);
+    lbm::mask_nearest_kernel<<<grid2, 128, 0, h->stream>>>(h->code, h->pitch, d_xs, d_ys, tw, th, d_small, d_cnt);
+    int solids = 0;
+    CUDA_TRY(cudaMemcpyAsync(&solids, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->launches++;
+    // no solid or no fluid pixel: scipy's transform of an image without background is an artefact of its algorithm, not
+    // a distance -- the caller reproduces it with scipy itself
+    *degenerate = (solids == 0 || (size_t)solids == n) ? 1 : 0;
+    if (*degenerate) return LBM_OK;
+    lbm::edt_columns_kernel<<<(tw + 127) / 128, 128, 0, h->stream>>>(d_small, tw, th, 1, d_g);   // fluid pixels: distance to the nearest solid
+    lbm::edt_rows_kernel<<<grid2, 128, 0, h->stream>>>(d_g, tw, th, d_df);
+    lbm::edt_columns_kernel<<<(tw + 127) / 128, 128, 0, h->stream>>>(d_small, tw, th, 0, d_g);   // solid pixels: distance to the nearest fluid
+    lbm::edt_rows_kernel<<<grid2, 128, 0, h->stream>>>(d_g, tw, th, d_ds);
+    lbm::sdf_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_small, d_df, d_ds, (long long)n, d_out);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 5;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, 2 * n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
 int lbm_device_view(LbmHandle h, LbmDeviceView *out) {
     if (int rc = check_handle(h, false)) return rc;
     if (!out) return fail(LBM_ERR_INVALID, "out is null");

@@ -233,4 +233,56 @@ __global__ void viz_fields_kernel(const float *__restrict__ vx, const float *__r
     vor[o] = __fsub_rn(dudy, dvdx);
 }
 
+// ---- static mask + signed distance field of the case file (io/lbm_writer.py:74-110) ------------------------------
+// small[y][x] = mask(x0 + xs[x], y0 + ys[y]) -- cv2.INTER_NEAREST of the transposed ROI (index tables from the host, see
+// lbm_static_mask); image order (th, tw).
+__global__ void mask_nearest_kernel(const uint8_t *__restrict__ code, int pitch, const int *__restrict__ xs,
+                                    const int *__restrict__ ys, int tw, int th, uint8_t *__restrict__ small, int *counts) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= tw) return;
+    const uint8_t v = code[(long long)xs[x] * pitch + ys[y]] & 1;
+    small[(long long)y * tw + x] = v;
+    if (v) atomicAdd(counts, 1);
+}
+// Exact Euclidean distance transform, scipy.ndimage.distance_transform_edt semantics: for every pixel that is NOT
+// background, the distance to the nearest background pixel (0 on the background).  Two separable passes on integers:
+// per column the distance along y to the nearest background pixel of that column, then per pixel the minimum over the
+// row of dx^2 + g^2; the square root is taken in double like scipy's.  bg = the value of `small` that is background.
+__global__ void edt_columns_kernel(const uint8_t *__restrict__ small, int tw, int th, int bg, int *__restrict__ g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= tw) return;
+    const int kInf = 1 << 20;
+    int d = kInf;
+    for (int y = 0; y < th; ++y) {
+        d = small[(long long)y * tw + x] == bg ? 0 : (d >= kInf ? kInf : d + 1);
+        g[(long long)y * tw + x] = d;
+    }
+    d = kInf;
+    for (int y = th - 1; y >= 0; --y) {
+        d = small[(long long)y * tw + x] == bg ? 0 : (d >= kInf ? kInf : d + 1);
+        if (d < g[(long long)y * tw + x]) g[(long long)y * tw + x] = d;
+    }
+}
+__global__ void edt_rows_kernel(const int *__restrict__ g, int tw, int th, double *__restrict__ dist) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= tw) return;
+    const int *row = g + (long long)y * tw;
+    long long best = -1;
+    for (int q = 0; q < tw; ++q) {
+        const long long gy = row[q];
+        if (gy >= (1 << 20)) continue;
+        const long long dx = x - q, d2 = dx * dx + gy * gy;
+        if (best < 0 || d2 < best) best = d2;
+    }
+    dist[(long long)y * tw + x] = sqrt((double)best);
+}
+// out (2, th, tw): channel 0 = mask, channel 1 = float32(dist_fluid - dist_solid)  (fluid positive)
+__global__ void sdf_combine_kernel(const uint8_t *__restrict__ small, const double *__restrict__ d_fluid,
+                                   const double *__restrict__ d_solid, long long n, float *__restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = small[i] ? 1.0f : 0.0f;
+    out[n + i] = __double2float_rn(__dsub_rn(d_fluid[i], d_solid[i]));
+}
+
 }  // namespace lbm

@@ -141,7 +141,7 @@ __host__ __device__ inline int ring_cell_count(int il0, int il_step, int il_coun
 }
 
 template <bool STRICT, bool EMIT, bool BB>
-__device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vmax, int &vnan) {
+__device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp, float &vmax, int &vnan) {
     const int ny = a.ny, pitch = a.pitch, n = a.il_count;
     const long long plane = a.plane;
     // decode: ring cell (ilr, jr), its owner (ilo, jo), boundary side dr; corners chain W/E -> top/bottom
@@ -180,7 +180,6 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vma
 #pragma unroll
     for (int k = 0; k < 9; ++k) me.f[k] = g[k];
     macro_from_f<STRICT>(g, me.rho, me.ux, me.uy);
-    const float ramp = a.ramp;
     const int igo = a.x_off + ilo, igr = a.x_off + ilr;
     cell_rest(r);
     bc_core(a.phys, dr, igr, igo, me, r, ramp);
@@ -210,6 +209,138 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float &vma
         const float m2 = __fadd_rn(__fmul_rn(r.ux, r.ux), __fmul_rn(r.uy, r.uy));
         vnan |= (m2 != m2);
         vmax = fmaxf(vmax, m2);
+    }
+}
+
+// Interior warp: one 64-cell segment of one interior column (see step_kernel).  `edge_w` / `edge_e`: the column is a slab
+// edge on the peer-memory path (warp-uniform) and its outgoing populations also go to the neighbour's halo column.
+template <bool STRICT, bool EMIT, bool BB>
+__device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg, int lane, bool edge_w, bool edge_e,
+                                              float &vmax, int &vnan) {
+    const int j0 = seg * kSegCells + lane * 2;                          // < pitch: the pitch is a multiple of 64
+    const int ny = a.ny;
+    const int t = il * a.pitch + j0;                                     // cell offset inside a plane (< 2^31, checked at create)
+
+    // pull (ref:254-257): fin[k] = f_k(i - e_kx, j - e_ky) for j = j0, j0 + 1; every load issued before the first use
+    float2 v[9];
+    float edge[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float *p = a.srcp[k] + t;
+        v[k] = LBM_LD(reinterpret_cast<const float2 *>(p));
+        edge[k] = 0.f;
+        // segment ends: the value of the neighbouring segment (seg 0 / the last one: a ring or padding cell's input, unused)
+        if (kEy[k] == 1 && lane == 0 && seg > 0) edge[k] = LBM_LD(p - 1);
+        if (kEy[k] == -1 && lane == 31) edge[k] = LBM_LD(p + 2);   // at most one float past the row: inside the allocation
+    }
+    // No `live` branch: lanes in the padding of the last segment (ny % 64 != 0) run the same code on the rest-state
+    // values the padding holds (init_kernel) and store nothing -- a branch here makes ptxas sink the three loads that
+    // feed no shuffle below the shuffles, i.e. behind a full memory latency (4.5 us of a 186 us step).
+    const float dx = __ldg(a.damp_x + il);
+    const float2 dy = __ldg(reinterpret_cast<const float2 *>(a.damp_y + j0));
+    // solid bits of the warp's 64 cells = 2 consecutive words; a lane's 2 cells sit in one of them
+    const unsigned code2 = (__ldg(a.code_bits + (t >> 5)) >> (j0 & 31)) & 3u;
+    unsigned char links[2] = {0, 0};
+    if (BB) {
+        const uchar2 l2 = __ldg(reinterpret_cast<const uchar2 *>(a.links8 + t));
+        links[0] = l2.x;
+        links[1] = l2.y;
+    }
+    float fin[2][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (kEy[k] == 0) {
+            fin[0][k] = v[k].x;
+            fin[1][k] = v[k].y;
+        } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
+            float below = __shfl_up_sync(0xffffffffu, v[k].y, 1);
+            if (lane == 0) below = edge[k];
+            fin[0][k] = below;
+            fin[1][k] = v[k].x;
+        } else {                   // needs j+1: first element of the lane above
+            float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
+            if (lane == 31) above = edge[k];
+            fin[0][k] = v[k].y;
+            fin[1][k] = above;
+        }
+    }
+    {
+        if (BB) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (links[c]) bounce_back(a, links[c], (long long)t + c, fin[c]);
+        }
+        // collide (ref:266-420)
+        float g[2][9];
+        if (STRICT) {
+            f32x2 f2[9], g2[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f2[k] = pack2(fin[0][k], fin[1][k]);
+            collide_strict_t<Lane2>(a.phys, f2, pack2(fmaxf(dx, dy.x), fmaxf(dx, dy.y)), g2);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) unpack2(g2[k], g[0][k], g[1][k]);
+        } else {
+            collide_fast(a.phys, fin[0], fmaxf(dx, dy.x), g[0]);
+            collide_fast(a.phys, fin[1], fmaxf(dx, dy.y), g[1]);
+        }
+        // rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
+        float rho[2] = {0.f, 0.f}, ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
+        if (EMIT || code2) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const bool solid = (code2 >> c) & 1u;
+                if (EMIT || solid) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+                if (solid) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
+                    ux[c] = 0.0f; uy[c] = 0.0f;
+                    if (BB) rho[c] = 1.0f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+                }
+            }
+        }
+        const bool lo_int = j0 >= 1 && j0 <= ny - 2, hi_int = j0 + 1 <= ny - 2;   // interior cells (ring cells: ring warps)
+        if (lo_int && hi_int) {            // the common case: one 64-bit store per plane
+#pragma unroll
+            for (int k = 0; k < 9; ++k) *reinterpret_cast<float2 *>(a.dstp[k] + t) = make_float2(g[0][k], g[1][k]);
+            if (EMIT) {
+                *reinterpret_cast<float2 *>(a.rho + t) = make_float2(rho[0], rho[1]);
+                *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
+                *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
+            }
+        } else if (lo_int || hi_int) {     // the pair shares a ring cell (ring warps write it) or padding: cell by cell
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (!(c == 0 ? lo_int : hi_int)) continue;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
+                if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
+            }
+        }
+        if (edge_w || edge_e) {            // the neighbour's halo column: the same cells, the three planes it will pull
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? edge_w : edge_e)) continue;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int k = kHaloPlane[side][q];
+                    float *p = a.peer_dst[side][q] + j0;
+                    if (lo_int && hi_int) *reinterpret_cast<float2 *>(p) = make_float2(g[0][k], g[1][k]);
+                    else {
+                        if (lo_int) p[0] = g[0][k];
+                        if (hi_int) p[1] = g[1][k];
+                    }
+                }
+            }
+        }
+        if (EMIT) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (!(c == 0 ? lo_int : hi_int)) continue;
+                const float m2 = vmag2_strict(ux[c], uy[c]);
+                vnan |= (m2 != m2);
+                vmax = fmaxf(vmax, m2);
+            }
+        }
     }
 }
 
@@ -272,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
     if (we_row) {
         // ------------------------------- ring warps: W / E columns and corners -----------------
         const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, vmax, vnan);
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, a.ramp, vmax, vnan);
     } else if (tb_row) {
         // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
         const int c = grp * kRingGroup + lane;
@@ -294,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
                 __syncthreads();
             }
             if (threadIdx.x < 64 && c < a.il_count)
-                ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, vmax, vnan);
+                ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, a.ramp, vmax, vnan);
             if (edge_here[0] || edge_here[1]) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -306,132 +437,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
         }
     } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
         // ------------------------------- interior warps --------------------------------------
-        const int il = il_cta;                                               // local column
-        const int j0 = seg * kSegCells + lane * 2;                          // < pitch: the pitch is a multiple of 64
-        const int ny = a.ny;
-        const int t = il * a.pitch + j0;                                     // cell offset inside a plane (< 2^31, checked at create)
-
-        // pull (ref:254-257): fin[k] = f_k(i - e_kx, j - e_ky) for j = j0, j0 + 1; every load issued before the first use
-        float2 v[9];
-        float edge[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float *p = a.srcp[k] + t;
-            v[k] = LBM_LD(reinterpret_cast<const float2 *>(p));
-            edge[k] = 0.f;
-            // segment ends: the value of the neighbouring segment (seg 0 / the last one: a ring or padding cell's input, unused)
-            if (kEy[k] == 1 && lane == 0 && seg > 0) edge[k] = LBM_LD(p - 1);
-            if (kEy[k] == -1 && lane == 31) edge[k] = LBM_LD(p + 2);   // at most one float past the row: inside the allocation
-        }
-        // No `live` branch: lanes in the padding of the last segment (ny % 64 != 0) run the same code on the rest-state
-        // values the padding holds (init_kernel) and store nothing -- a branch here makes ptxas sink the three loads that
-        // feed no shuffle below the shuffles, i.e. behind a full memory latency (4.5 us of a 186 us step).
-        const float dx = __ldg(a.damp_x + il);
-        const float2 dy = __ldg(reinterpret_cast<const float2 *>(a.damp_y + j0));
-        // solid bits of the warp's 64 cells = 2 consecutive words; a lane's 2 cells sit in one of them
-        const unsigned code2 = (__ldg(a.code_bits + (t >> 5)) >> (j0 & 31)) & 3u;
-        unsigned char links[2] = {0, 0};
-        if (BB) {
-            const uchar2 l2 = __ldg(reinterpret_cast<const uchar2 *>(a.links8 + t));
-            links[0] = l2.x;
-            links[1] = l2.y;
-        }
-        float fin[2][9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (kEy[k] == 0) {
-                fin[0][k] = v[k].x;
-                fin[1][k] = v[k].y;
-            } else if (kEy[k] == 1) {  // needs j-1: last element of the lane below
-                float below = __shfl_up_sync(0xffffffffu, v[k].y, 1);
-                if (lane == 0) below = edge[k];
-                fin[0][k] = below;
-                fin[1][k] = v[k].x;
-            } else {                   // needs j+1: first element of the lane above
-                float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
-                if (lane == 31) above = edge[k];
-                fin[0][k] = v[k].y;
-                fin[1][k] = above;
-            }
-        }
-        {
-            if (BB) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    if (links[c]) bounce_back(a, links[c], (long long)t + c, fin[c]);
-            }
-            // collide (ref:266-420)
-            float g[2][9];
-            if (STRICT) {
-                f32x2 f2[9], g2[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) f2[k] = pack2(fin[0][k], fin[1][k]);
-                collide_strict_t<Lane2>(a.phys, f2, pack2(fmaxf(dx, dy.x), fmaxf(dx, dy.y)), g2);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) unpack2(g2[k], g[0][k], g[1][k]);
-            } else {
-                collide_fast(a.phys, fin[0], fmaxf(dx, dy.x), g[0]);
-                collide_fast(a.phys, fin[1], fmaxf(dx, dy.y), g[1]);
-            }
-            // rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
-            float rho[2] = {0.f, 0.f}, ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
-            if (EMIT || code2) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const bool solid = (code2 >> c) & 1u;
-                    if (EMIT || solid) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
-                    if (solid) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
-                        ux[c] = 0.0f; uy[c] = 0.0f;
-                        if (BB) rho[c] = 1.0f;
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
-                    }
-                }
-            }
-            const bool lo_int = j0 >= 1 && j0 <= ny - 2, hi_int = j0 + 1 <= ny - 2;   // interior cells (ring cells: ring warps)
-            if (lo_int && hi_int) {            // the common case: one 64-bit store per plane
-#pragma unroll
-                for (int k = 0; k < 9; ++k) *reinterpret_cast<float2 *>(a.dstp[k] + t) = make_float2(g[0][k], g[1][k]);
-                if (EMIT) {
-                    *reinterpret_cast<float2 *>(a.rho + t) = make_float2(rho[0], rho[1]);
-                    *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
-                    *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
-                }
-            } else if (lo_int || hi_int) {     // the pair shares a ring cell (ring warps write it) or padding: cell by cell
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (!(c == 0 ? lo_int : hi_int)) continue;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
-                    if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
-                }
-            }
-            if (edge_w || edge_e) {            // the neighbour's halo column: the same cells, the three planes it will pull
-#pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    if (!(side == 0 ? edge_w : edge_e)) continue;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int k = kHaloPlane[side][q];
-                        float *p = a.peer_dst[side][q] + j0;
-                        if (lo_int && hi_int) *reinterpret_cast<float2 *>(p) = make_float2(g[0][k], g[1][k]);
-                        else {
-                            if (lo_int) p[0] = g[0][k];
-                            if (hi_int) p[1] = g[1][k];
-                        }
-                    }
-                }
-            }
-            if (EMIT) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (!(c == 0 ? lo_int : hi_int)) continue;
-                    const float m2 = vmag2_strict(ux[c], uy[c]);
-                    vnan |= (m2 != m2);
-                    vmax = fmaxf(vmax, m2);
-                }
-            }
-        }
+        interior_warp<STRICT, EMIT, BB>(a, il_cta, seg, lane, edge_w, edge_e, vmax, vnan);
     }
 
     if (EMIT) {  // whole warp: max over lanes, one atomic per warp and only if it raises the running max

@@ -209,7 +209,8 @@ class DeviceLBMCaseWriter:
             return
         if self._mask is not None and self.static_mask is None:
             sv = self._solver
-            if sv is not None and hasattr(sv, "static_mask_fields") and getattr(sv, "world", 1) == 1:
+            binary = self._mask.dtype == bool or bool(np.isin(self._mask, (0, 1)).all())   # the device holds mask == 1
+            if binary and sv is not None and hasattr(sv, "static_mask_fields") and getattr(sv, "world", 1) == 1:
                 self.static_mask = sv.static_mask_fields(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
             else:
                 self.static_mask = static_mask_host(self._mask, self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)

@@ -46,11 +46,25 @@ class _NoBar:
         pass
 
 
-def run_simulation_loop(config, solver, viz, recorder, gui, writer, max_steps, progress=True):
+def get_zone_config(config):
+    """utils/config_utils.py:22-50 of the reference: sponge widths and the ROI rectangle for the GUI overlay."""
+    nx, ny = config["simulation"]["nx"], config["simulation"]["ny"]
+    z = config["domain_zones"]
+    return {"sponge_in": z["sponge_in"], "sponge_out": z["sponge_out"], "sponge_top": z["sponge_top"], "sponge_bot": z["sponge_bot"],
+            "roi_x_start": z["sponge_in"] + z["buffer"], "roi_x_end": nx - z["sponge_out"] - z["buffer"],
+            "roi_y_start": z["sponge_bot"] + z["buffer"], "roi_y_end": ny - z["sponge_top"] - z["buffer"], "nx": nx, "ny": ny}
+
+
+def run_simulation_loop(config, solver, viz, recorder, gui, writer, max_steps, progress=True, draw_zone_overlay=None):
     """ops:60-242.  Returns the metadata dict the batch runner reads (status / reason / final_steps /
-    target_steps / re_val / u_max / D / nu)."""
+    target_steps / re_val / u_max / D / nu).
+
+    `draw_zone_overlay(gui, zones, y_offset=...)`: the reference's `utils.draw_zone_overlay` (visualization/viz_utils.py:52;
+    Taichi GUI line drawing, outside this package) -- pass it to get the overlay of ops:155-157; without it the overlay
+    is skipped, everything else is the reference's decision logic."""
     sim_cfg = config["simulation"]
     out_cfg = config["outputs"]
+    zones = get_zone_config(config)   # ops:67
     step = sim_cfg["compute_step_size"]
     gui_every = out_cfg["gui"]["interval_steps"]
     vid_every = out_cfg["video"]["interval_steps"]
@@ -90,16 +104,19 @@ def run_simulation_loop(config, solver, viz, recorder, gui, writer, max_steps, p
             gui_frame = out_cfg["gui"]["enable"] and done % gui_every == 0
             vid_frame = out_cfg["video"]["enable"] and done % vid_every == 0 and done >= start_record
             img = None
-            if (gui_frame or vid_frame) and viz is not None:
+            if gui_frame or vid_frame:   # like ops:145-148, a frame without a `viz` is an error (status "Error")
                 if hasattr(viz, "process_frame_from_solver"):   # device-side fields (gui_viz.DeviceGuiViz)
                     img = viz.process_frame_from_solver(solver)
                 else:
                     vel, mask = solver.get_physical_fields()
                     img = viz.process_frame(vel, mask)
-            if gui_frame and gui and img is not None:
+            if gui_frame and gui:
                 gui.set_image(img)
+                if out_cfg["gui"]["show_zone_overlay"] and draw_zone_overlay is not None:   # ops:155-157
+                    draw_zone_overlay(gui, zones, y_offset=0.0)
+                    draw_zone_overlay(gui, zones, y_offset=0.5)
                 gui.show()
-            if vid_frame and recorder and img is not None:
+            if vid_frame and recorder:
                 recorder.write_frame(np.transpose(img, (1, 0, 2)))
             timings["viz"] = (time.perf_counter() - t0) * 1e3
 

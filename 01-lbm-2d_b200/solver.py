@@ -248,6 +248,20 @@ class LBM2D_MRT_LES:
         return {"running_sum": rs, "running_vel_sq_sum": vs, "sum_abs_vor": vo, "global_min": mn, "global_max": mx,
                 "running_count": int(cnt.value)}
 
+    def static_mask_fields(self, x0, x1, y0, y1, target_w, target_h):
+        """(2, H, W) float32 `static_mask` of the case file (io/lbm_writer.py:74-110: nearest-resized ROI mask + signed
+        distance field), computed on the device from the resident mask; bit-identical to cv2 + scipy.  The degenerate
+        masks (no solid / no fluid pixel in the ROI), where scipy's output is an artefact, go through scipy itself."""
+        out = np.empty((2, int(target_h), int(target_w)), np.float32)
+        deg = C.c_int32(0)
+        _capi.check(self._lib.lbm_static_mask(self._h, int(x0), int(x1), int(y0), int(y1), int(target_w), int(target_h),
+                                              out.ctypes.data_as(C.c_void_p), C.byref(deg)))
+        if deg.value:
+            from .device_writer import static_mask_host
+
+            return static_mask_host(self.mask.to_numpy() == 1.0, x0, x1, y0, y1, target_w, target_h)
+        return out
+
     # ------------------------------------------------------------------ extras
     def get_viz_fields(self, sigma=None):
         """(vel_mag, vorticity), (nx, ny) float32 each: the numeric part of the reference's video frame

@@ -43,6 +43,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_CELL = 72.0  # 9 fp32 reads + 9 fp32 writes
 METRIC = "MLUPS (fused D2Q9 MRT-LES step)"
+BASELINE_CONFIG = {"cylinder": "configs[0]", "tube_bank": "configs[1]", "urban": "configs[2]", "random": "configs[3]",
+                   "sweep_case": "configs[4], one case"}
 N_WINDOWS = 25
 MIN_WARMUP_STEPS = 200
 
@@ -118,6 +120,8 @@ def build_workload(name, n_gpus):
 
     if name == "random":  # BASELINE configs[3]: fixed 32768x8192 grid -> strong scaling over the slabs
         return W.random_obstacles()
+    if name == "sweep_case":  # one of the 64 procedural 1024x256 cases of BASELINE configs[4] (step timing)
+        return W.sweep_case(0)
     if name == "urban" and n_gpus > 1:
         # weak scaling: every GPU gets THE configs[2] block pattern (the 8192x2048 mask tiled along x), so the work per
         # GPU -- solid fraction included -- is exactly that of the N = 1 run; inlet on the first slab, outlet on the last
@@ -410,8 +414,8 @@ def run_ours(args):
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload} {nx}x{ny} (BASELINE configs[2] per GPU" + (", its mask tiled along x" if world > 1 else "") +
-                        "), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
+            "workload": f"{args.workload} {nx}x{ny} (BASELINE {BASELINE_CONFIG.get(args.workload, 'configs[2]')}" +
+                        (" per GPU, its mask tiled along x" if world > 1 else "") + "), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
             "grid": [nx, ny], "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, 1 halo column / step, halo path: {halo_path}",
             "l2_policy": "working set 1.22 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
             "arith": args.arith, "kernel": args.kernel, "solid_fraction": float(mask.mean()),
@@ -449,13 +453,27 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--windows", type=int, default=N_WINDOWS, help="back-to-back timed windows of --steps steps each")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank", "random"])
+    ap.add_argument("--workload", default="urban", choices=["urban", "cylinder", "tube_bank", "random", "sweep_case", "sweep"])
     ap.add_argument("--grid", default=None, help="NXxNY: urban-style obstacles on a custom grid (experiments)")
     ap.add_argument("--quick", action="store_true", help="timed region only (profiling runs): no e2e full-frame / alt / cpu legs")
     ap.add_argument("--no-alt", action="store_true", help="skip the measurement of the other arithmetic")
+    ap.add_argument("--concurrency", type=int, default=2, help="--workload sweep: cases in flight per GPU")
     ap.add_argument("--arith", default="strict", choices=["fast", "strict"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "register", "tma"])
     args = ap.parse_args()
+    if args.workload == "sweep":   # BASELINE configs[4]: cases/hour in replica mode (no slabs, no collective on the data path)
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the sweep metric (cases/hour incl. export) has no CPU arm here; "
+                              "use the default workload for the reference arm"}))
+            return
+        batch = importlib.import_module("01-lbm-2d_b200.batch")
+        batch.run_sweep(n_cases=32 * max(1, int(os.environ.get("WORLD_SIZE", "1"))), out_dir=os.path.join(tempfile.gettempdir(), "lbm_sweep"),
+                        concurrency=args.concurrency)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

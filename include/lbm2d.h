@@ -166,6 +166,14 @@ int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw
 int lbm_comm_unique_id(uint8_t out[LBM_COMM_ID_BYTES]);
 int lbm_comm_connect(LbmHandle h, int rank, int nranks, const uint8_t id[LBM_COMM_ID_BYTES]);
 
+/* `static_mask` of the case file, io/lbm_writer.py:74-110: the ROI [x0,x1) x [y0,y1) of the obstacle mask, transposed to
+ * image order and resized to (target_h, target_w) with cv2.INTER_NEAREST, and its signed Euclidean distance field
+ * (scipy distance_transform_edt of the fluid minus that of the solid: positive in the fluid) -- out is (2, th, tw)
+ * float32, bit-identical to the reference's cv2 + scipy result.  *degenerate = 1 (out untouched) when the resized mask
+ * has no solid or no fluid pixel; the binding then falls back to cv2 + scipy.  Single GPU. */
+int lbm_static_mask(LbmHandle h, int32_t x0, int32_t x1, int32_t y0, int32_t y1, int32_t target_w, int32_t target_h,
+                    float *out, int32_t *degenerate);
+
 /* Peer-memory halo path (preferred on NVLink / NVSwitch nodes): after lbm_comm_connect(), every rank exports CUDA IPC
  * handles of its two population buffers and its inbox counters (lbm_peer_export), the host exchanges the blobs
  * (torch.distributed all_gather) and each rank maps its neighbours' buffers (lbm_peer_connect; NULL on a side that is a

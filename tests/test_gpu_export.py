@@ -79,3 +79,28 @@ def test_export_fast_arithmetic_within_tolerance_and_run_loop_uses_it(pkg, tmp_p
     assert rel_linf(got["turbulence"], want["turbulence"]) <= 1e-5
     assert rel_linf(got["mean_vel_field"], want["mean_vel_field"]) <= 1e-5
     assert np.abs(got["mean_vel_sq_field"] - want["mean_vel_sq_field"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("nx,ny,roi,target", [
+    (300, 140, (20, 260, 10, 130), (160, 80)),      # ratio 1.5
+    (257, 99, (5, 250, 3, 97), (113, 43)),          # awkward fractional ratios
+    (512, 128, (16, 448, 8, 120), (246, 64)),       # BASELINE configs[0] geometry
+    (200, 96, (0, 200, 0, 96), (200, 96)),          # identity
+])
+def test_static_mask_and_sdf_on_the_device_match_cv2_and_scipy(pkg, nx, ny, roi, target):
+    """(f)-4 / row a19: nearest-resized ROI mask + signed distance field computed from the resident mask, bit-identical to
+    the reference's cv2.INTER_NEAREST + scipy.ndimage.distance_transform_edt chain (io/lbm_writer.py:74-110)."""
+    dw = importlib.import_module("01-lbm-2d_b200.device_writer")
+    mask = cylinder_mask(nx, ny, nx // 3, ny // 2, ny // 7) | random_blocks_mask(nx, ny, 14, seed=ny, smin=2, smax=17, keep_in=0, keep_out=0)
+    mask[roi[0] + 3, roi[2]:roi[3]] = True                      # a wall across the ROI, solids on the ROI border
+    s = pkg.LBM2D_MRT_LES(make_config(nx, ny), mask_data=mask)
+    x0, x1, y0, y1 = roi
+    got = s.static_mask_fields(x0, x1, y0, y1, *target)
+    want = dw.static_mask_host(mask, x0, x1, y0, y1, *target)
+    assert got.shape == want.shape == (2, target[1], target[0]) and got.dtype == np.float32
+    assert np.array_equal(got[0], want[0]), "mask"
+    assert np.array_equal(got[1], want[1]), float(np.abs(got[1] - want[1]).max())
+    # degenerate ROI (no solid inside): scipy's artefact is reproduced through the host path
+    empty = pkg.LBM2D_MRT_LES(make_config(nx, ny), mask_data=np.zeros((nx, ny), bool))
+    assert np.array_equal(empty.static_mask_fields(x0, x1, y0, y1, *target),
+                          dw.static_mask_host(np.zeros((nx, ny), bool), x0, x1, y0, y1, *target))

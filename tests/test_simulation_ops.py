@@ -126,3 +126,36 @@ def test_video_frames_take_the_device_fields_when_the_viz_offers_them():
     assert len([c for c in s2.calls if c[0] == "fields"]) == 2 and not [c for c in s2.calls if c[0] == "viz_fields"]
     with pytest.raises(TypeError):
         viz.process_frame(None, None)
+
+
+def test_gui_frames_draw_the_zone_overlay_twice_like_the_reference():
+    """ops:152-158: set_image, the overlay for both halves of the window when `show_zone_overlay` is on, show()."""
+
+    class Gui:
+        running, log = True, []
+
+        def set_image(self, img):
+            self.log.append("img")
+
+        def show(self):
+            self.log.append("show")
+
+    class HostViz:
+        def process_frame(self, vel, mask):
+            return np.zeros((8, 8, 3), np.float32)
+
+    class S(ScriptedSolver):
+        def get_physical_fields(self):
+            return np.zeros((self.nx, self.ny, 2), np.float32), np.zeros((self.nx, self.ny), np.float32)
+
+    cfg = _cfg()
+    cfg["outputs"]["gui"].update(enable=True, interval_steps=20, show_zone_overlay=True)
+    gui, overlay = Gui(), []
+    draw = lambda g, zones, y_offset=0.0: (overlay.append((y_offset, zones["roi_x_start"], zones["roi_x_end"])), g.log.append("ovl"))  # noqa: E731
+    ops.run_simulation_loop(cfg, S(lambda n: 0.1), HostViz(), None, gui, None, max_steps=40, progress=False, draw_zone_overlay=draw)
+    assert gui.log == ["img", "ovl", "ovl", "show"] * 2 and [o[0] for o in overlay] == [0.0, 0.5] * 2
+    z = cfg["domain_zones"]
+    assert overlay[0][1:] == (z["sponge_in"] + z["buffer"], cfg["simulation"]["nx"] - z["sponge_out"] - z["buffer"])
+    # a frame is due but there is no viz object: the reference fails inside the loop and reports status "Error"
+    meta = ops.run_simulation_loop(cfg, S(lambda n: 0.1), None, None, Gui(), None, max_steps=40, progress=False)
+    assert meta["status"] == "Error"
