@@ -454,10 +454,12 @@ int exchange_halos(LbmSolver *s, float *buf, cudaStream_t st) {
 }
 
 typedef void (*StepFn)(const lbm::StepArgs);
-StepFn step_fn(bool strict, bool emit, bool bb = false) {
-#define LBM_PICK(S, E) (bb ? (StepFn)lbm::step_kernel<S, E, true> : (StepFn)lbm::step_kernel<S, E, false>)
+StepFn step_fn(bool strict, bool emit, bool bb = false, bool peer = false) {
+#define LBM_PICK2(S, E, B) (peer ? (StepFn)lbm::step_kernel<S, E, B, true> : (StepFn)lbm::step_kernel<S, E, B, false>)
+#define LBM_PICK(S, E) (bb ? LBM_PICK2(S, E, true) : LBM_PICK2(S, E, false))
     return strict ? (emit ? LBM_PICK(true, true) : LBM_PICK(true, false)) : (emit ? LBM_PICK(false, true) : LBM_PICK(false, false));
 #undef LBM_PICK
+#undef LBM_PICK2
 }
 
 // Launch one step of the register variant.  `pdl`: programmatic dependent launch -- the grid may start being
@@ -933,7 +935,7 @@ int lbm_run(LbmHandle h, int steps) {
             // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
             a.early_rows = (pdl && early_cols > 0) ? a_all.ring_row0 : 0;
             a.progress_expected = h->progress_total;
-            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr), blocks, st, a, pdl));
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr, h->peer_mode), blocks, st, a, pdl));
             if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;

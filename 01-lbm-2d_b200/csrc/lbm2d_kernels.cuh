@@ -140,7 +140,7 @@ __host__ __device__ inline int ring_cell_count(int il0, int il_step, int il_coun
     return 2 * il_count + (w ? ny : 0) + (e ? ny : 0);   // (ny - 2) column cells + 2 corners per side
 }
 
-template <bool STRICT, bool EMIT, bool BB>
+template <bool STRICT, bool EMIT, bool BB, bool PEER>
 __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp, float &vmax, int &vnan) {
     const int ny = a.ny, pitch = a.pitch, n = a.il_count;
     const long long plane = a.plane;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp
     int ilr, jr, ilo, jo, dr, corner_dr = -1;
     if (idx < 2 * n) {
         const bool top = idx < n;
-        ilo = ilr = col_to_il(a, top ? idx : idx - n);
+        ilo = ilr = PEER ? col_to_il(a, top ? idx : idx - n) : a.il0 + (top ? idx : idx - n) * a.il_step;
         jo = top ? ny - 2 : 1;
         jr = top ? ny - 1 : 0;
         dr = top ? 1 : 3;
@@ -196,6 +196,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.dst[k * plane + o] = r.f[k];
+    if (PEER)
 #pragma unroll
     for (int side = 0; side < 2; ++side)   // top / bottom cell of an edge column: also part of the neighbour's halo column
         if (ilr == a.edge_il[side]) {
@@ -214,7 +215,7 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp
 
 // Interior warp: one 64-cell segment of one interior column (see step_kernel).  `edge_w` / `edge_e`: the column is a slab
 // edge on the peer-memory path (warp-uniform) and its outgoing populations also go to the neighbour's halo column.
-template <bool STRICT, bool EMIT, bool BB>
+template <bool STRICT, bool EMIT, bool BB, bool PEER>
 __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg, int lane, bool edge_w, bool edge_e,
                                               float &vmax, int &vnan) {
     const int j0 = seg * kSegCells + lane * 2;                          // < pitch: the pitch is a multiple of 64
@@ -354,7 +355,8 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
 // halves of packed fp32 pairs (Lane2).  Ring warps (their own grid rows: one row behind every 32 columns for the
 // top / bottom cells, one block of rows for the W / E columns): one ring cell per lane, see above.
 // BB: optional half-way bounce-back obstacle mode (not the reference's).
-template <bool STRICT, bool EMIT, bool BB = false>
+// PEER: x-slab launch on the peer-memory halo path (edge-column waits / remote stores / counters compiled in).
+template <bool STRICT, bool EMIT, bool BB = false, bool PEER = false>
 __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs a) {
     // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows (columns and ring rows, see below)
     const int row = blockIdx.y + blockIdx.z * 65535;
@@ -391,9 +393,9 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
     int vnan = 0;
     // slab edge column (CTA-uniform; both false off the peer-memory slab path): wait for the neighbour's previous step
     const bool col_cta = !we_row && !tb_row && col < a.il_count;
-    const int il_cta = col_cta ? col_to_il(a, col) : -2;
-    const bool edge_w = il_cta == a.edge_il[0], edge_e = il_cta == a.edge_il[1];
-    if (edge_w || edge_e) {
+    const int il_cta = col_cta ? (PEER ? col_to_il(a, col) : a.il0 + col * a.il_step) : -2;
+    const bool edge_w = PEER && il_cta == a.edge_il[0], edge_e = PEER && il_cta == a.edge_il[1];
+    if (PEER && (edge_w || edge_e)) {
         if (threadIdx.x == 0) {
             if (edge_w) inbox_wait(a, 0);
             if (edge_e) inbox_wait(a, 1);
@@ -403,30 +405,30 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
     if (we_row) {
         // ------------------------------- ring warps: W / E columns and corners -----------------
         const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB>(a, idx, a.ramp, vmax, vnan);
+        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB, PEER>(a, idx, a.ramp, vmax, vnan);
     } else if (tb_row) {
         // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
         const int c = grp * kRingGroup + lane;
         if (blockIdx.x == 0) {
             // does this group hold an edge column?  (CTA-uniform)  Its ring cells read the halo and go to the neighbour too.
-            const int c0 = grp * kRingGroup, c1 = min(c0 + kRingGroup, a.il_count);
-            bool edge_here[2];
+            bool edge_here[2] = {false, false};
+            if (PEER) {
+                const int c0 = grp * kRingGroup, c1 = min(c0 + kRingGroup, a.il_count);
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                edge_here[side] = false;
-                if (a.edge_il[side] >= 0)
-                    for (int cc = c0; cc < c1; ++cc) edge_here[side] |= col_to_il(a, cc) == a.edge_il[side];
-            }
-            if (edge_here[0] || edge_here[1]) {
-                if (threadIdx.x == 0) {
-                    if (edge_here[0]) inbox_wait(a, 0);
-                    if (edge_here[1]) inbox_wait(a, 1);
+                for (int side = 0; side < 2; ++side)
+                    if (a.edge_il[side] >= 0)
+                        for (int cc = c0; cc < c1; ++cc) edge_here[side] |= col_to_il(a, cc) == a.edge_il[side];
+                if (edge_here[0] || edge_here[1]) {
+                    if (threadIdx.x == 0) {
+                        if (edge_here[0]) inbox_wait(a, 0);
+                        if (edge_here[1]) inbox_wait(a, 1);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             if (threadIdx.x < 64 && c < a.il_count)
-                ring_cell<STRICT, EMIT, BB>(a, (threadIdx.x >> 5) * a.il_count + c, a.ramp, vmax, vnan);
-            if (edge_here[0] || edge_here[1]) {
+                ring_cell<STRICT, EMIT, BB, PEER>(a, (threadIdx.x >> 5) * a.il_count + c, a.ramp, vmax, vnan);
+            if (PEER && (edge_here[0] || edge_here[1])) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     __threadfence_system();
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
         }
     } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
         // ------------------------------- interior warps --------------------------------------
-        interior_warp<STRICT, EMIT, BB>(a, il_cta, seg, lane, edge_w, edge_e, vmax, vnan);
+        interior_warp<STRICT, EMIT, BB, PEER>(a, il_cta, seg, lane, edge_w, edge_e, vmax, vnan);
     }
 
     if (EMIT) {  // whole warp: max over lanes, one atomic per warp and only if it raises the running max
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs
             if (any_nan) a.maxv_bits[1] = 1u;
         }
     }
-    if (edge_w || edge_e) {   // edge-column CTA: its part of the neighbour's halo column is complete
+    if (PEER && (edge_w || edge_e)) {   // edge-column CTA: its part of the neighbour's halo column is complete
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();

@@ -405,3 +405,20 @@ def test_long_unsteady_run_mean_fields_within_1e3(pkg, tmp_path):
         assert rel_linf(a["mean_vel_field"][ch], b["mean_vel_field"][ch]) <= 1e-3, ch
     assert rel_linf(a["mean_vel_field"], b["mean_vel_field"]) <= 1e-3
     assert rel_linf(a["mean_vel_sq_field"], b["mean_vel_sq_field"]) <= 2e-3
+
+
+def test_inline_packed_division_equals_the_lane_wise_library_path(pkg, config1_oracle, monkeypatch):
+    """LBM2D_NO_FAST_DIV=1 sends every division / square root of the strict kernel through __fdiv_rn / __fsqrt_rn (the
+    code the inline FFMA2 sequences fall back to outside their guarded range): same bits, and both equal the oracle."""
+    cfg, mask, ref, _ = config1_oracle
+    outs = []
+    for off in (False, True):
+        monkeypatch.delenv("LBM2D_NO_FAST_DIV", raising=False)
+        if off:
+            monkeypatch.setenv("LBM2D_NO_FAST_DIV", "1")
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask)
+        s.init()
+        s.run_step(1000)
+        outs.append(s.f_old.to_numpy())
+        s.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], ref.f_old)
