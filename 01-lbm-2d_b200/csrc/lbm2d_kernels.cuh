@@ -16,7 +16,10 @@ namespace lbm {
 #define LBM_WPB 4
 #endif
 #ifndef LBM_MINB
-#define LBM_MINB 10
+#define LBM_MINB 10          // fast arithmetic: 48 registers, 40 resident warps per SM (profiles/r01_tuning_sweep.md)
+#endif
+#ifndef LBM_MINB_STRICT
+#define LBM_MINB_STRICT 9    // strict arithmetic: 56 registers, 36 warps: -5 % step time (profiles/r02_tuning.md)
 #endif
 constexpr int kWarpsPerBlock = LBM_WPB;
 static_assert(LBM_WPB >= 2, "the top / bottom ring row of a group needs two warps");
@@ -213,6 +216,59 @@ __device__ __forceinline__ void ring_cell(const StepArgs &a, int idx, float ramp
     }
 }
 
+// Stores of one thread's two cells (j0, j0 + 1 of local column t / pitch): the nine populations, on EMIT steps rho / u and
+// the max|u|^2 bookkeeping, on a slab edge column (peer-memory path) also the neighbour's halo column.
+template <bool EMIT, bool PEER>
+__device__ __forceinline__ void store_cells(const StepArgs &a, int t, int j0, const float (&g)[2][9], const float (&rho)[2],
+                                            const float (&ux)[2], const float (&uy)[2], bool edge_w, bool edge_e, float &vmax,
+                                            int &vnan) {
+    const int ny = a.ny;
+    (void)ny;
+    const bool lo_int = j0 >= 1 && j0 <= ny - 2, hi_int = j0 + 1 <= ny - 2;   // interior cells (ring cells: ring warps)
+    if (lo_int && hi_int) {            // the common case: one 64-bit store per plane
+#pragma unroll
+        for (int k = 0; k < 9; ++k) *reinterpret_cast<float2 *>(a.dstp[k] + t) = make_float2(g[0][k], g[1][k]);
+        if (EMIT) {
+            *reinterpret_cast<float2 *>(a.rho + t) = make_float2(rho[0], rho[1]);
+            *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
+            *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
+        }
+    } else if (lo_int || hi_int) {     // the pair shares a ring cell (ring warps write it) or padding: cell by cell
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!(c == 0 ? lo_int : hi_int)) continue;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
+            if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
+        }
+    }
+    if (PEER && (edge_w || edge_e)) {   // the neighbour's halo column: the same cells, the three planes it will pull
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (!(side == 0 ? edge_w : edge_e)) continue;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int k = kHaloPlane[side][q];
+                float *p = a.peer_dst[side][q] + j0;
+                if (lo_int && hi_int) *reinterpret_cast<float2 *>(p) = make_float2(g[0][k], g[1][k]);
+                else {
+                    if (lo_int) p[0] = g[0][k];
+                    if (hi_int) p[1] = g[1][k];
+                }
+            }
+        }
+    }
+    if (EMIT) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!(c == 0 ? lo_int : hi_int)) continue;
+            const float m2 = vmag2_strict(ux[c], uy[c]);
+            vnan |= (m2 != m2);
+            vmax = fmaxf(vmax, m2);
+        }
+    }
+}
+
 // Interior warp: one 64-cell segment of one interior column (see step_kernel).  `edge_w` / `edge_e`: the column is a slab
 // edge on the peer-memory path (warp-uniform) and its outgoing populations also go to the neighbour's halo column.
 template <bool STRICT, bool EMIT, bool BB, bool PEER>
@@ -257,11 +313,11 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
             float below = __shfl_up_sync(0xffffffffu, v[k].y, 1);
             if (lane == 0) below = edge[k];
             fin[0][k] = below;
-            fin[1][k] = v[k].x;
+            fin[1][k] = STRICT ? opaque_copy(v[k].x) : v[k].x;   // see opaque_copy(): the pair (below, v.x) in natural order
         } else {                   // needs j+1: first element of the lane above
             float above = __shfl_down_sync(0xffffffffu, v[k].x, 1);
             if (lane == 31) above = edge[k];
-            fin[0][k] = v[k].y;
+            fin[0][k] = STRICT ? opaque_copy(v[k].y) : v[k].y;
             fin[1][k] = above;
         }
     }
@@ -284,9 +340,13 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
             collide_fast(a.phys, fin[0], fmaxf(dx, dy.x), g[0]);
             collide_fast(a.phys, fin[1], fmaxf(dx, dy.y), g[1]);
         }
-        // rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill
+        // rho / u (ref:425-436) only where consumed: EMIT steps and the obstacle refill.  The common case -- no solid
+        // cell in the pair, no EMIT -- stores straight from the collision's registers; the other path has its own copy of
+        // the stores (a shared tail would cost a register move per value at the merge: 14 MOVs on the hot path).
         float rho[2] = {0.f, 0.f}, ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
-        if (EMIT || code2) {
+        if (!EMIT && code2 == 0) {
+            store_cells<EMIT, PEER>(a, t, j0, g, rho, ux, uy, edge_w, edge_e, vmax, vnan);
+        } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const bool solid = (code2 >> c) & 1u;
@@ -298,49 +358,7 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
                     for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
                 }
             }
-        }
-        const bool lo_int = j0 >= 1 && j0 <= ny - 2, hi_int = j0 + 1 <= ny - 2;   // interior cells (ring cells: ring warps)
-        if (lo_int && hi_int) {            // the common case: one 64-bit store per plane
-#pragma unroll
-            for (int k = 0; k < 9; ++k) *reinterpret_cast<float2 *>(a.dstp[k] + t) = make_float2(g[0][k], g[1][k]);
-            if (EMIT) {
-                *reinterpret_cast<float2 *>(a.rho + t) = make_float2(rho[0], rho[1]);
-                *reinterpret_cast<float2 *>(a.ux + t) = make_float2(ux[0], ux[1]);
-                *reinterpret_cast<float2 *>(a.uy + t) = make_float2(uy[0], uy[1]);
-            }
-        } else if (lo_int || hi_int) {     // the pair shares a ring cell (ring warps write it) or padding: cell by cell
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (!(c == 0 ? lo_int : hi_int)) continue;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) a.dstp[k][t + c] = g[c][k];
-                if (EMIT) { a.rho[t + c] = rho[c]; a.ux[t + c] = ux[c]; a.uy[t + c] = uy[c]; }
-            }
-        }
-        if (edge_w || edge_e) {            // the neighbour's halo column: the same cells, the three planes it will pull
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                if (!(side == 0 ? edge_w : edge_e)) continue;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int k = kHaloPlane[side][q];
-                    float *p = a.peer_dst[side][q] + j0;
-                    if (lo_int && hi_int) *reinterpret_cast<float2 *>(p) = make_float2(g[0][k], g[1][k]);
-                    else {
-                        if (lo_int) p[0] = g[0][k];
-                        if (hi_int) p[1] = g[1][k];
-                    }
-                }
-            }
-        }
-        if (EMIT) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (!(c == 0 ? lo_int : hi_int)) continue;
-                const float m2 = vmag2_strict(ux[c], uy[c]);
-                vnan |= (m2 != m2);
-                vmax = fmaxf(vmax, m2);
-            }
+            store_cells<EMIT, PEER>(a, t, j0, g, rho, ux, uy, edge_w, edge_e, vmax, vnan);
         }
     }
 }
@@ -357,7 +375,7 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
 // BB: optional half-way bounce-back obstacle mode (not the reference's).
 // PEER: x-slab launch on the peer-memory halo path (edge-column waits / remote stores / counters compiled in).
 template <bool STRICT, bool EMIT, bool BB = false, bool PEER = false>
-__global__ void __launch_bounds__(kThreads, LBM_MINB) step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB) step_kernel(const StepArgs a) {
     // grid: x = blocks of segments down a column, y (+ z beyond 65535) = rows (columns and ring rows, see below)
     const int row = blockIdx.y + blockIdx.z * 65535;
     // Programmatic dependent launch: this grid is scheduled while the previous step drains, and waits here
