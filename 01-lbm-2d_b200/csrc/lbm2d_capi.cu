@@ -293,6 +293,7 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.progress = s->progress;
     a.col_split = -1;
     a.edge_il[0] = a.edge_il[1] = -1;
+    a.edge_row[0] = a.edge_row[1] = -1;
     a.phys = s->phys;
     if (s->peer_mode) {
         // grid order [1 .. E | W/E ring block | nx_local - 2 | E + 1 .. nx_local - 3] (set by lbm_run through col_split)
@@ -908,6 +909,17 @@ int lbm_run(LbmHandle h, int steps) {
         lbm::StepArgs a = make_args(h);
         if (col_split >= 0) { a.col_split = col_split; }
         else if (h->peer_mode) { a.col_split = ncols; }   // identity order il = 1 + col
+        if (h->peer_mode) {   // grid rows of the edge columns: col -> row = groups of 33, shifted past the W/E ring block
+            auto row_of = [&](int col) {
+                const int vrow = col / lbm::kRingGroup * (lbm::kRingGroup + 1) + col % lbm::kRingGroup;
+                return vrow < a_all.ring_row0 ? vrow : vrow + a_all.ring_rows;
+            };
+            if (a.edge_il[0] >= 0) a.edge_row[0] = row_of(a.col_split == 0 ? 1 : 0);             // il = 1
+            if (a.edge_il[1] >= 0) a.edge_row[1] = row_of(a.col_split < ncols ? a.col_split : ncols - 1);   // il = nx_local - 2
+            if (ncols == 1)   // one owned column: it is both edges
+                for (int side = 0; side < 2; ++side)
+                    if (a.edge_il[side] >= 0) a.edge_row[side] = row_of(0);
+        }
         const bool overlap = !h->peer_mode && h->comm && h->nranks > 1 && h->nx_local >= 6 && h->stream_e;
         cudaStream_t st = h->stream;
         dim3 blocks = blocks_all;
@@ -935,7 +947,9 @@ int lbm_run(LbmHandle h, int steps) {
             // early start only straight behind a step that signalled (it > 0: the previous launch of this loop)
             a.early_rows = (pdl && early_cols > 0) ? a_all.ring_row0 : 0;
             a.progress_expected = h->progress_total;
-            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr, h->peer_mode), blocks, st, a, pdl));
+            static const bool force_peer_kernel = std::getenv("LBM2D_FORCE_PEER_KERNEL") != nullptr;   // experiment: cost of the PEER code on one GPU
+            if (force_peer_kernel && !h->peer_mode) a.col_split = ncols;
+            CUDA_TRY(launch_step(step_fn(strict, emit, h->links8 != nullptr, h->peer_mode || force_peer_kernel), blocks, st, a, pdl));
             if (!overlap) h->progress_total += signals_all;
         }
         h->steps_done++;

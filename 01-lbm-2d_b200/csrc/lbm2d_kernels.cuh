@@ -70,6 +70,7 @@ struct StepArgs {
     // touch their own halo they wait until their inbox shows that the neighbour's edge CTAs of the PREVIOUS step are
     // done (which also means the neighbour no longer reads the halo column this step overwrites).  side 0 = west.
     int edge_il[2];                       // local column of the edge on that side, or -1 (domain boundary / no peer mode)
+    int edge_row[2];                      // the grid row (blockIdx.y + 65535 blockIdx.z) of that column, or -1
     float *peer_dst[2][3];                // neighbour's halo column in ITS destination buffer, planes kHaloPlane[side][.]
     unsigned long long *peer_inbox[2];    // the neighbour's counter this rank adds to
     const unsigned long long *inbox;      // this rank's counters [2]: written by the west / east neighbour
@@ -410,9 +411,11 @@ __global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB)
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
     // slab edge column (CTA-uniform; both false off the peer-memory slab path): wait for the neighbour's previous step
-    const bool col_cta = !we_row && !tb_row && col < a.il_count;
-    const int il_cta = col_cta ? (PEER ? col_to_il(a, col) : a.il0 + col * a.il_step) : -2;
-    const bool edge_w = PEER && il_cta == a.edge_il[0], edge_e = PEER && il_cta == a.edge_il[1];
+    // The two edge columns sit in grid rows the host knows (edge_row[side], -1 = none): two uniform compares per CTA
+    // decide; every other column maps with one compare (col_to_il's middle case IS the east edge row).
+    const bool edge_w = PEER && row == a.edge_row[0], edge_e = PEER && row == a.edge_row[1];
+    const int il_cta = !PEER ? a.il0 + col * a.il_step
+                             : ((edge_w || edge_e) ? (edge_e ? a.edge_il[1] : a.edge_il[0]) : (col < a.col_split ? col + 1 : col));
     if (PEER && (edge_w || edge_e)) {
         if (threadIdx.x == 0) {
             if (edge_w) inbox_wait(a, 0);
@@ -420,17 +423,17 @@ __global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB)
         }
         __syncthreads();
     }
-    if (we_row) {
-        // ------------------------------- ring warps: W / E columns and corners -----------------
-        const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
-        if (idx < a.n_ring) ring_cell<STRICT, EMIT, BB, PEER>(a, idx, a.ramp, vmax, vnan);
-    } else if (tb_row) {
-        // ------------------------------- ring warps: top (warp 0) / bottom (warp 1) of one group
-        const int c = grp * kRingGroup + lane;
-        if (blockIdx.x == 0) {
-            // does this group hold an edge column?  (CTA-uniform)  Its ring cells read the halo and go to the neighbour too.
-            bool edge_here[2] = {false, false};
-            if (PEER) {
+    if (we_row || tb_row) {
+        // ------------------------------- ring warps (ONE call site of ring_cell: it is ~1 500 instructions) ----------
+        int ring_idx = -1;
+        bool edge_here[2] = {false, false};
+        if (we_row) {   // W / E columns and corners
+            const int idx = 2 * a.il_count + (ring_rel * (int)gridDim.x * kWarpsPerBlock + seg) * 32 + lane;
+            if (idx < a.n_ring) ring_idx = idx;
+        } else if (blockIdx.x == 0) {   // top (warp 0) / bottom (warp 1) cells of one group of 32 columns
+            const int c = grp * kRingGroup + lane;
+            if (threadIdx.x < 64 && c < a.il_count) ring_idx = (threadIdx.x >> 5) * a.il_count + c;
+            if (PEER) {   // does this group hold a slab edge column?  (CTA-uniform)  Its ring cells read the halo and go to the neighbour too.
                 const int c0 = grp * kRingGroup, c1 = min(c0 + kRingGroup, a.il_count);
 #pragma unroll
                 for (int side = 0; side < 2; ++side)
@@ -444,20 +447,42 @@ __global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB)
                     __syncthreads();
                 }
             }
-            if (threadIdx.x < 64 && c < a.il_count)
-                ring_cell<STRICT, EMIT, BB, PEER>(a, (threadIdx.x >> 5) * a.il_count + c, a.ramp, vmax, vnan);
-            if (PEER && (edge_here[0] || edge_here[1])) {
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    __threadfence_system();
-                    if (edge_here[0]) atomicAdd_system(a.peer_inbox[0], 1ULL);
-                    if (edge_here[1]) atomicAdd_system(a.peer_inbox[1], 1ULL);
-                }
+        }
+        if (ring_idx >= 0) ring_cell<STRICT, EMIT, BB, PEER>(a, ring_idx, a.ramp, vmax, vnan);
+        if (PEER && (edge_here[0] || edge_here[1])) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                if (edge_here[0]) atomicAdd_system(a.peer_inbox[0], 1ULL);
+                if (edge_here[1]) atomicAdd_system(a.peer_inbox[1], 1ULL);
             }
         }
     } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
         // ------------------------------- interior warps --------------------------------------
-        interior_warp<STRICT, EMIT, BB, PEER>(a, il_cta, seg, lane, edge_w, edge_e, vmax, vnan);
+        // slab edge columns (2 of thousands) take their own copy of the interior code with the neighbour stores compiled
+        // in; every other column runs exactly the single-GPU code (sharing one copy cost 3.4 % of the step on ALL columns)
+        interior_warp<STRICT, EMIT, BB, false>(a, il_cta, seg, lane, false, false, vmax, vnan);
+        // A slab edge column also goes to the neighbour's halo column: every thread forwards the three populations of
+        // ITS OWN two cells, re-read from the destination buffer (a thread sees its own stores).  A second copy of the
+        // interior code with the remote stores inlined measured 1.1 % slower on EVERY column (instruction cache).
+        if (PEER && (edge_w || edge_e)) {
+            const int j0 = seg * kSegCells + lane * 2, t = il_cta * a.pitch + j0;
+            const bool lo_int = j0 >= 1 && j0 <= a.ny - 2, hi_int = j0 + 1 <= a.ny - 2;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? edge_w : edge_e)) continue;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float *src = a.dstp[kHaloPlane[side][q]] + t;
+                    float *dst = a.peer_dst[side][q] + j0;
+                    if (lo_int && hi_int) *reinterpret_cast<float2 *>(dst) = __ldcg(reinterpret_cast<const float2 *>(src));
+                    else {
+                        if (lo_int) dst[0] = __ldcg(src);
+                        if (hi_int) dst[1] = __ldcg(src + 1);
+                    }
+                }
+            }
+        }
     }
 
     if (EMIT) {  // whole warp: max over lanes, one atomic per warp and only if it raises the running max

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+run() { tag=$1; shift; env "$@" python bench.py --quick --steps 1000 --windows 3 --warmup 100 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$tag', round(d['ms_per_step']*1000,2))"; }
+for i in 1 2; do run plain A=1; run peer_kernel LBM2D_FORCE_PEER_KERNEL=1; done

@@ -45,3 +45,14 @@ def test_slabs_over_nccl_fallback_path(world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, LBM2D_HALO="nccl"))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("SLAB-OK") == 2 and "halo=nccl" in res.stdout and "SLAB-EXTRAS-OK" in res.stdout
+
+
+def test_configs3_full_grid_on_slabs():
+    """BASELINE configs[3] at its stated size, 32768x8192 random obstacles, on 2 x-slabs (tests/slab_full_worker.py)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "slab_full_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "SLAB-FULL-OK" in res.stdout and "halo=peer" in res.stdout, res.stdout[-2000:]
