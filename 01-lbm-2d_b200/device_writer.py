@@ -75,7 +75,7 @@ class _RawContainer:
         self.fh = open(self.stem + ".turbulence.f32", "wb")
 
     def append(self, frame):
-        self.fh.write(np.ascontiguousarray(frame, np.float32).tobytes())
+        np.ascontiguousarray(frame, np.float32).tofile(self.fh)   # no intermediate bytes object
         self.fh.flush()
         self.n += 1
 
