@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <sys/mman.h>
@@ -111,6 +112,10 @@ struct LbmSolver {
     bool use_pdl = true;
     long long early_min_ctas = 2500;      // grids with fewer CTAs keep the plain PDL hand-over
     int early_target = 1500;              // CTAs that may start on the progress counter (0 = early start off)
+    // Launch-bound grids: a whole lbm_run(steps) batch is replayed as ONE CUDA graph (see lbm_run); key = steps * 2 + parity
+    bool use_graph = true;
+    int graph_min_steps = 8;
+    std::map<long long, cudaGraphExec_t> graphs;
     unsigned long long *progress = nullptr;   // device counter, see step_kernel
     unsigned long long progress_total = 0;    // its value once every step launched so far has signalled
     int tma_grid = 0;
@@ -149,6 +154,7 @@ struct LbmSolver {
         for (cudaEvent_t ev : {ev_m, ev_e, ev_e_prev, ev_x})
             if (ev) cudaEventDestroy(ev);
         if (stream_e) cudaStreamDestroy(stream_e);
+        for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
         for (void *ptr : {(void *)f[0], (void *)f[1], (void *)code, (void *)damp_x, (void *)damp_y, (void *)ramp_tab,
                           (void *)ctr, (void *)mac, (void *)ring_ctx, (void *)maxv, (void *)links,
                           (void *)force_partial, (void *)force_out, (void *)staging, (void *)exp_xtab, (void *)exp_ytab,
@@ -700,6 +706,8 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
         (void)tiles;
         s->use_tma = p.kernel == LBM_KERNEL_TMA;
         s->use_pdl = !std::getenv("LBM2D_NO_PDL");
+        s->use_graph = !std::getenv("LBM2D_NO_GRAPH");
+        if (const char *e = std::getenv("LBM2D_GRAPH_MIN_STEPS")) s->graph_min_steps = std::max(1, std::atoi(e));
         if (const char *e = std::getenv("LBM2D_EARLY_CTAS")) s->early_target = std::max(0, std::atoi(e));
         if (const char *e = std::getenv("LBM2D_EARLY_MIN_CTAS")) s->early_min_ctas = std::max(0, std::atoi(e));
         if (p.kernel < LBM_KERNEL_AUTO || p.kernel > LBM_KERNEL_TMA) {
@@ -881,6 +889,15 @@ int lbm_run(LbmHandle h, int steps) {
         CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));
         h->ev_e_prev_valid = false;
     }
+    // Launch-bound grids (no early start: under ~2 waves of CTAs a step is a few microseconds, about what one launch costs
+    // the host): once the soft-start ramp has reached its final value every per-step kernel argument repeats with the
+    // buffer parity, so the whole batch -- K - 1 plain steps chained by programmatic edges, the max|u| reset, the EMIT
+    // step -- is captured ONCE per (K, parity) and replayed with ONE cudaGraphLaunch per lbm_run: the host cost of a batch
+    // no longer grows with K, which is what lets several cases in flight (one stream each, batch.py) fill the GPU
+    // instead of queueing on the context's launch lock.  The diagnostic step counter is set behind the graph.
+    const bool graphable = h->use_graph && !h->use_tma && !(h->comm && h->nranks > 1) && !h->peer_mode && early_cols == 0 &&
+                           steps >= h->graph_min_steps && h->steps_done + 1 >= (int64_t)h->p.warmup_steps;
+    auto enqueue = [&](bool in_graph) -> int {
     for (int it = 0; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
@@ -907,6 +924,7 @@ int lbm_run(LbmHandle h, int steps) {
             continue;
         }
         lbm::StepArgs a = make_args(h);
+        if (in_graph) { a.bump_ctr = 0; a.frame = 0; }   // nothing in a replayed node may depend on the step index
         if (col_split >= 0) { a.col_split = col_split; }
         else if (h->peer_mode) { a.col_split = ncols; }   // identity order il = 1 + col
         if (h->peer_mode) {   // grid rows of the edge columns: col -> row = groups of 33, shifted past the W/E ring block
@@ -962,6 +980,36 @@ int lbm_run(LbmHandle h, int steps) {
         } else if (!h->peer_mode) {
             if (int rc = exchange_halos(h, a.dst, h->stream)) return rc;
         }
+    }
+    return LBM_OK;
+    };
+    if (!graphable) {
+        if (int rc = enqueue(false)) return rc;
+    } else {
+        const long long key = (long long)steps * 2 + (long long)(h->steps_done & 1);
+        auto hit = h->graphs.find(key);
+        if (hit == h->graphs.end()) {
+            // thread-local capture: other cases (threads) of the same process keep allocating / launching meanwhile
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t done0 = h->steps_done, total0 = h->steps_total, launches0 = h->launches;
+            const int rc = enqueue(true);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            h->steps_done = done0; h->steps_total = total0; h->launches = launches0;   // nothing has run yet
+            if (rc != LBM_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return rc; }
+            if (ce != cudaSuccess) return fail(LBM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(LBM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+            hit = h->graphs.emplace(key, exec).first;
+        }
+        CUDA_TRY(cudaGraphLaunch(hit->second, h->stream));
+        h->steps_done += steps;
+        h->steps_total += steps;
+        h->launches += steps;
+        lbm::set_counter_kernel<<<1, 1, 0, h->stream>>>(h->ctr + (h->steps_done & 1), (int)h->steps_done);
+        h->launches++;
     }
     if (h->peer_mode && steps > 0) h->halo_wait_pending = true;   // see halo_ready()
     if (!h->peer_mode && h->comm && h->nranks > 1 && h->stream_e) {  // later work on the main stream sees the last exchange

@@ -520,6 +520,9 @@ __global__ void halo_wait_kernel(const StepArgs a) {
     }
 }
 
+// Graph replay of a batch (lbm_run): the replayed step nodes carry no step index, the diagnostic counter is set behind them.
+__global__ void set_counter_kernel(int *ctr, int value) { *ctr = value; }
+
 // Self test of Lane2's inline division / square root (lbm_selftest_arith): random operands from the guarded box
 // against __fdiv_rn / __fsqrt_rn, bit for bit.  out[0..2] = mismatches of a / b (b in [1/8, 8]), 1 / t (t in
 // [2^-10, 2^40]) and sqrt(x).

@@ -13,11 +13,13 @@ Like the reference, the file is opened in the constructor and every frame is app
 reference's AsyncLBMCaseWriter, writer:260-296): host memory stays bounded however long the case runs, a killed run
 leaves its frames on disk, and file I/O overlaps the next batch of steps.
 
-Container.  HDF5 through h5py, as in the reference (`container="h5"`).  h5py is absent from the build image, so
-there is a second, explicitly named container for such hosts: `container="raw"` streams the frames to
-`<stem>.turbulence.f32` (append-only float32) and writes the remaining datasets and attributes to `<stem>.npz` at
-`finalize()`; `read_case()` reads either back into the same dict.  `container="auto"` (default) picks h5 when h5py
-imports and raw otherwise, and says so once on stderr -- the raw container is a fallback, not the format.
+Container.  The case file is HDF5 on every host.  `container="h5"`: through h5py, as in the reference.  h5py / libhdf5 are
+absent from the build image, so `container="h5lite"` writes the same file -- same dataset names, shapes, dtypes, the
+resizable one-frame-per-chunk `turbulence`, the root attributes -- with the package's own dependency-free HDF5 writer
+(`h5lite.py`: the classic on-disk format every libhdf5 reads; frames uncompressed, because the reference's `lzf` is an
+h5py plug-in filter).  `container="auto"` (default) picks h5 when h5py imports and h5lite otherwise.  `container="raw"`
+(`<stem>.turbulence.f32` + `<stem>.npz`) is kept as an explicitly requested scratch format only.  `read_case()` reads
+any of them back into the same dict.
 """
 from __future__ import annotations
 
@@ -28,6 +30,8 @@ import sys
 import threading
 
 import numpy as np
+
+from . import h5lite
 
 try:
     import h5py
@@ -64,6 +68,31 @@ class _H5Container:
         self.f.close()
 
 
+class _H5LiteContainer:
+    """The same HDF5 file without h5py (h5lite.py): frames go straight to the end of the file, one chunk each; the
+    chunk index, the statistics datasets and the attributes are written by finalize()."""
+
+    def __init__(self, path, channels, th, tw, compression, static_mask):
+        self.w = h5lite.Writer(path)
+        if static_mask is not None:
+            self.w.create_dataset("static_mask", static_mask, "f4")
+        self.dset = self.w.create_appendable("turbulence", (channels, th, tw), "f4")
+
+    def append(self, frame):
+        self.dset.append(frame)
+        self.w.flush()
+
+    def finalize(self, datasets, attrs):
+        for k, v in datasets.items():
+            self.w.create_dataset(k, v)
+        for k, v in attrs.items():
+            self.w.set_attr(k, v)
+        self.w.close()
+
+    def abort(self):
+        self.w.abort()
+
+
 class _RawContainer:
     """h5py-free streaming container: frames appended to <stem>.turbulence.f32, the rest in <stem>.npz."""
 
@@ -93,10 +122,14 @@ def read_case(path):
     """Datasets (+ `attrs`) of a finished case as a dict, from whichever container `path` (with or without extension)
     was written to.  `turbulence` comes back as an array for h5 and as a read-only memmap for the raw container."""
     stem = os.path.splitext(path)[0] if path.endswith((".h5", ".npz")) else path
-    if h5py is not None and os.path.exists(stem + ".h5"):
-        with h5py.File(stem + ".h5", "r") as f:
-            out = {k: f[k][...] for k in f.keys()}
-            out["attrs"] = {k: f.attrs[k] for k in f.attrs.keys()}
+    if os.path.exists(stem + ".h5") and not os.path.exists(stem + ".npz"):
+        if h5py is not None:
+            with h5py.File(stem + ".h5", "r") as f:
+                out = {k: f[k][...] for k in f.keys()}
+                out["attrs"] = {k: f.attrs[k] for k in f.attrs.keys()}
+            return out
+        out = h5lite.read(stem + ".h5")
+        out.pop("dataset_attrs", None)
         return out
     z = np.load(stem + ".npz")
     out = {k: z[k] for k in z.files if not k.startswith("attr_") and k != "turbulence_shape"}
@@ -188,15 +221,15 @@ class DeviceLBMCaseWriter:
     def _pick_container(kind):
         global _warned
         if kind == "h5" and h5py is None:
-            raise ImportError("container='h5' needs h5py (as the reference's LBMCaseWriter does); use container='raw' "
-                              "for the h5py-free streaming container")
+            raise ImportError("container='h5' needs h5py (as the reference's LBMCaseWriter does); use container='h5lite' "
+                              "for the built-in HDF5 writer")
         if kind == "auto":
-            kind = "h5" if h5py is not None else "raw"
-            if kind == "raw" and not _warned:
+            kind = "h5" if h5py is not None else "h5lite"
+            if kind == "h5lite" and not _warned:
                 _warned = True
-                print("[DeviceLBMCaseWriter] h5py is not importable: writing <stem>.turbulence.f32 + <stem>.npz "
-                      "(container='raw') instead of HDF5; read with device_writer.read_case()", file=sys.stderr)
-        if kind not in ("h5", "raw"):
+                print("[DeviceLBMCaseWriter] h5py is not importable: the HDF5 case file is written by the built-in "
+                      "writer (container='h5lite': same datasets and attributes, frames uncompressed)", file=sys.stderr)
+        if kind not in ("h5", "h5lite", "raw"):
             raise ValueError(f"unknown container {kind!r}")
         return kind
 
@@ -215,7 +248,7 @@ class DeviceLBMCaseWriter:
             else:
                 self.static_mask = static_mask_host(self._mask, self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
         if self._is_writer_rank():
-            cls = _H5Container if self._container_kind == "h5" else _RawContainer
+            cls = {"h5": _H5Container, "h5lite": _H5LiteContainer, "raw": _RawContainer}[self._container_kind]
             self._container = cls(self.file_path, self.channels, self.target_h, self.target_w, self.compression, self.static_mask)
             self._appender = _AsyncAppender(self._container)
 

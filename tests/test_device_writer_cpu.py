@@ -45,7 +45,7 @@ def _case(tmp_path, container, monkeypatch):
                                              container=container)
 
 
-@pytest.mark.parametrize("container", ["h5", "raw"])
+@pytest.mark.parametrize("container", ["h5", "h5lite", "raw"])
 def test_frames_are_streamed_and_the_reference_dataset_set_is_written(tmp_path, monkeypatch, container):
     cfg, mask, w = _case(tmp_path, container, monkeypatch)
     assert not hasattr(w, "frames")                      # nothing accumulates on the host
@@ -56,6 +56,11 @@ def test_frames_are_streamed_and_the_reference_dataset_set_is_written(tmp_path, 
             d = fake_h5py.FILES[str(tmp_path / "case.h5")]["turbulence"]
             assert d.shape[0] == i + 1 and d.maxshape[0] is None and d.chunks == (1, 9, w.target_h, w.target_w)
             assert d.compression == "lzf"
+        elif container == "h5lite":                      # ... and at the end of the real file, one chunk per frame
+            fb = 9 * w.target_h * w.target_w * 4
+            assert os.path.getsize(tmp_path / "case.h5") == 512 + 2 * w.target_h * w.target_w * 4 + (i + 1) * fb
+            tail = np.fromfile(tmp_path / "case.h5", np.float32, offset=os.path.getsize(tmp_path / "case.h5") - fb)
+            assert np.array_equal(tail.reshape(9, w.target_h, w.target_w), w.last_frame)
         else:
             assert os.path.getsize(tmp_path / "case.turbulence.f32") == (i + 1) * 9 * w.target_h * w.target_w * 4
     out = w.finalize()
@@ -83,8 +88,11 @@ def test_h5_container_needs_h5py_and_auto_says_what_it_does(tmp_path, monkeypatc
     cfg = make_config(120, 60, sponge=(6, 14, 3, 3), buffer=2, save_h=20)
     with pytest.raises(ImportError):
         dw.DeviceLBMCaseWriter(str(tmp_path / "a.h5"), cfg, 120, 60, container="h5")
-    dw.DeviceLBMCaseWriter(str(tmp_path / "a.h5"), cfg, 120, 60).finalize()
-    assert "container='raw'" in capsys.readouterr().err
+    out = dw.DeviceLBMCaseWriter(str(tmp_path / "a.h5"), cfg, 120, 60).finalize()
+    assert "container='h5lite'" in capsys.readouterr().err
+    with open(tmp_path / "a.h5", "rb") as f:                   # without h5py the case file is still HDF5
+        assert f.read(8) == b"\x89HDF\r\n\x1a\n"
+    assert out["turbulence"].shape[0] == 0 and not os.path.exists(tmp_path / "a.npz")
 
 
 def _edt_brute(feature):

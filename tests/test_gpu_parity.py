@@ -376,6 +376,35 @@ def test_early_start_long_run_on_grids_of_a_few_waves(pkg, nx, ny, monkeypatch):
     assert np.isfinite(out[0]).all() and np.array_equal(out[0], out[1])
 
 
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("nx,ny,bc", [(512, 128, (0, 2, 1, 2)), (1024, 256, (0, 0, 1, 2)), (203, 130, (0, 2, 1, 0))])
+def test_graph_replay_of_a_batch_is_bit_identical_to_stream_launches(pkg, arith, nx, ny, bc, monkeypatch):
+    """Launch-bound grids replay a whole run_step(K) batch as one CUDA graph once the soft-start ramp is over (lbm_run).
+    Same state, bit for bit, as the plain PDL launches: even and odd K (both buffer parities are captured), batches
+    before / across / after the end of the ramp, a velocity-Dirichlet wall that reads the ramp, repeated replays."""
+    cfg = make_config(nx, ny, rho_in=1.01, nu=0.01, cs=0.1, warmup=40, sponge=(8, 32, 4, 4))
+    cfg["boundary_condition"]["type"] = list(bc)
+    cfg["boundary_condition"]["value"] = [[0.03, 0.0], [0.02, 0.0], [0.0, 0.0], [0.015, 0.0]]
+    mask = cylinder_mask(nx, ny, nx // 4, ny // 2 + 2, max(4, ny // 12))
+    outs = []
+    for no_graph in (False, True):
+        monkeypatch.delenv("LBM2D_NO_GRAPH", raising=False)
+        if no_graph:
+            monkeypatch.setenv("LBM2D_NO_GRAPH", "1")
+        s = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, arith=arith, kernel="register")
+        s.init()
+        got = []
+        for n in (10, 25, 25, 100, 100, 33, 33, 100, 9, 1, 100):   # 10 + 25: ramp (stream launches); from step 39 on: graphs
+            s.run_step(n)
+            got.append((s.get_max_velocity(), s.step_count(), tuple(s.get_force())))
+        outs.append((s.f_old.to_numpy(), s.rho.to_numpy(), s.vel.to_numpy(), got, s.launch_count()))
+        s.close()
+    a, b = outs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert a[3][-1][1] == 536 and np.isfinite(a[0]).all()
+    assert a[4] > b[4]   # the graph path did run: one counter kernel more per replayed batch
+
+
 # ------------------------------------------------------------------ long unsteady run: mean fields (north_star: <= 1e-3)
 def test_long_unsteady_run_mean_fields_within_1e3(pkg, tmp_path):
     """30 000 steps of an off-centre cylinder at Re ~ 100 (vortex shedding: the standard deviation of jx over the
