@@ -60,6 +60,7 @@ EXPORTS = {
     "lbm_export_configure": (C.c_int, [C.c_void_p, C.POINTER(LbmExportConfig)]),
     "lbm_export_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lbm_export_frame": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lbm_export_frame_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "lbm_export_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lbm_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

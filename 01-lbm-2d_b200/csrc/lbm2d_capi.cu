@@ -1051,7 +1051,7 @@ int lbm_synchronize(LbmHandle h) {
 int lbm_step_count(LbmHandle h, int64_t *steps) {
     if (int rc = check_handle(h, true)) return rc;
     if (!steps) return fail(LBM_ERR_INVALID, "steps is null");
-    int v = 0;  // read the device counter: it is what the kernels use for the ramp
+    int v = 0;  // the device copy of frame_count (diagnostic: written by the step kernels / behind a replayed graph)
     CUDA_TRY(cudaMemcpyAsync(&v, h->ctr + (h->steps_done & 1), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     *steps = v;
@@ -1319,7 +1319,18 @@ int lbm_export_layout(LbmHandle h, int32_t *dlo, int32_t *dhi, int32_t *target_h
     return LBM_OK;
 }
 
-int lbm_export_frame(LbmHandle h, float *out_chw) {
+static int export_frame_impl(LbmHandle h, float *out_chw);
+
+int lbm_export_frame(LbmHandle h, float *out_chw) { return export_frame_impl(h, out_chw); }
+
+int lbm_export_frame_device(LbmHandle h, const float **frame_chw_dev) {
+    if (!frame_chw_dev) return fail(LBM_ERR_INVALID, "frame_chw_dev is null");
+    if (int rc = export_frame_impl(h, nullptr)) return rc;
+    *frame_chw_dev = (h->exp_geom.dhi - h->exp_geom.dlo) > 0 ? h->exp_frame : nullptr;
+    return LBM_OK;
+}
+
+static int export_frame_impl(LbmHandle h, float *out_chw) {
     if (int rc = check_handle(h, true)) return rc;
     if (!h->exp_ready) return fail(LBM_ERR_STATE, "lbm_export_configure() has not been called");
     if (int rc = halo_ready(h)) return rc;

@@ -263,9 +263,10 @@ class DeviceLBMCaseWriter:
         if solver is not None and solver is not self._solver:
             self.attach(solver)
         sv = self._solver
-        frame = sv.export_frame()
         if getattr(sv, "world", 1) > 1:   # x-slabs: every rank holds a column range of the frame; rank 0 writes
-            frame = sv.gather_columns(frame)
+            frame = sv.export_frame_gathered() if hasattr(sv, "export_frame_gathered") else sv.gather_columns(sv.export_frame())
+        else:
+            frame = sv.export_frame()
         if self._container is not None:
             self._appender.append(frame)   # the frame is a fresh array: the worker thread owns it from here
         self.last_frame = frame

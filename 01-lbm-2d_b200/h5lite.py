@@ -302,10 +302,10 @@ class Writer:
 # ------------------------------------------------------------------------------------------------------- reader
 class _Reader:
     def __init__(self, path):
-        with open(path, "rb") as f:
-            self.buf = f.read()
+        # the file is mapped, not read: a case file is mostly `turbulence` frames, which `read` hands out as views
+        self.buf = np.memmap(path, np.uint8, "r") if os.path.getsize(path) else b""
         base = 0
-        while self.buf[base:base + 8] != SIGNATURE:     # a user block pushes the superblock to 512, 1024, 2048 ...
+        while bytes(self.buf[base:base + 8]) != SIGNATURE:     # a user block pushes the superblock to 512, 1024, 2048 ...
             base = 512 if base == 0 else base * 2
             if base + 8 > len(self.buf):
                 raise ValueError(f"{path}: no HDF5 signature")
@@ -336,7 +336,7 @@ class _Reader:
             q, left = blocks.pop(0)
             while left >= 8 and len(out) < nmsg:
                 mtype, msize, flags = struct.unpack_from("<HHB", b, q)
-                body = b[q + 8:q + 8 + msize]
+                body = bytes(b[q + 8:q + 8 + msize])
                 if mtype == MSG_CONTINUATION:
                     off, ln = struct.unpack_from("<QQ", body, 0)
                     blocks.append((self.at(off), ln))
@@ -348,15 +348,15 @@ class _Reader:
     # -- groups -----------------------------------------------------------------------------------------------
     def heap_name(self, heap_addr, offset):
         p = self.at(heap_addr)
-        if self.buf[p:p + 4] != b"HEAP":
+        if bytes(self.buf[p:p + 4]) != b"HEAP":
             raise ValueError("bad local heap signature")
         seg = self.at(struct.unpack_from("<Q", self.buf, p + 24)[0])
-        end = self.buf.index(b"\0", seg + offset)
-        return self.buf[seg + offset:end].decode("utf-8")
+        raw = bytes(self.buf[seg + offset:seg + offset + 1024])
+        return raw[:raw.index(b"\0")].decode("utf-8")
 
     def group_entries(self, btree_addr, heap_addr):
         b, p = self.buf, self.at(btree_addr)
-        if b[p:p + 4] != b"TREE":
+        if bytes(b[p:p + 4]) != b"TREE":
             raise ValueError("bad B-tree signature")
         ntype, level, used = struct.unpack_from("<BBH", b, p + 4)
         if ntype != 0:
@@ -369,7 +369,7 @@ class _Reader:
                 out += self.group_entries(child, heap_addr)
                 continue
             s = self.at(child)
-            if b[s:s + 4] != b"SNOD":
+            if bytes(b[s:s + 4]) != b"SNOD":
                 raise ValueError("bad symbol table node signature")
             for j in range(struct.unpack_from("<H", b, s + 6)[0]):
                 name_off, header, cache = struct.unpack_from("<QQI", b, s + 8 + 40 * j)
@@ -403,7 +403,7 @@ class _Reader:
 
     def global_heap_object(self, addr, index):
         b, p = self.buf, self.at(addr)
-        if b[p:p + 4] != b"GCOL":
+        if bytes(b[p:p + 4]) != b"GCOL":
             raise ValueError("bad global heap signature")
         size = struct.unpack_from("<Q", b, p + 8)[0]
         q = p + 16
@@ -412,7 +412,7 @@ class _Reader:
             if idx == 0:
                 break
             if idx == index:
-                return b[q + 16:q + 16 + osize]
+                return bytes(b[q + 16:q + 16 + osize])
             q += 16 + (osize + 7) // 8 * 8
         raise ValueError(f"global heap object {index} not found")
 
@@ -424,14 +424,14 @@ class _Reader:
                 ln, addr, idx = struct.unpack_from("<IQI", raw, 16 * i)
                 vals.append(self.global_heap_object(addr, idx)[:ln].decode("utf-8"))
             return vals[0] if not shape else np.array(vals, dtype=object).reshape(shape)
-        a = np.frombuffer(raw, dtype, count=int(np.prod(shape)) if shape else 1)
-        return a.reshape(shape).copy() if shape else a[0]
+        a = np.frombuffer(raw, dtype, count=int(np.prod(shape)) if shape else 1)   # a view when `raw` is the mapped file
+        return a.reshape(shape) if shape else a[0]
 
     # -- datasets ---------------------------------------------------------------------------------------------
     def chunks(self, btree_addr, rank1):
         """[(offsets, nbytes, filter_mask, address)] of a chunk B-tree, depth first."""
         b, p = self.buf, self.at(btree_addr)
-        if b[p:p + 4] != b"TREE":
+        if bytes(b[p:p + 4]) != b"TREE":
             raise ValueError("bad chunk B-tree signature")
         ntype, level, used = struct.unpack_from("<BBH", b, p + 4)
         if ntype != 1:
@@ -483,15 +483,21 @@ class _Reader:
             addr, size = struct.unpack_from("<QQ", layout, 2)
             if addr == UNDEF or n == 0:
                 return np.zeros(shape, dtype)
-            return self.decode(dtype, shape, self.buf[self.at(addr):self.at(addr) + n * itemsize])
+            return self.decode(dtype, shape, self.buf[self.at(addr):self.at(addr) + n * itemsize])   # a view of the map
         rank1 = layout[2]
         btree = struct.unpack_from("<Q", layout, 3)[0]
         cdims = struct.unpack_from(f"<{rank1}I", layout, 11)[:-1]
-        out = np.zeros(shape, dtype)
         if btree == UNDEF or n == 0:
-            return out
-        for offs, nbytes, fmask, addr in self.chunks(btree, rank1):
-            raw = self.buf[self.at(addr):self.at(addr) + nbytes]
+            return np.zeros(shape, dtype)
+        chunks = self.chunks(btree, rank1)
+        cbytes = int(np.prod(cdims)) * itemsize
+        if (not filters and tuple(cdims) == (1,) + tuple(shape[1:]) and len(chunks) == shape[0] and
+                all(c[0][0] == i and c[3] == chunks[0][3] + i * cbytes for i, c in enumerate(chunks))):
+            # one frame per chunk, stored back to back in arrival order (what the Writer produces): a view, no copy
+            return np.frombuffer(self.buf, dtype, count=n, offset=self.at(chunks[0][3])).reshape(shape)
+        out = np.zeros(shape, dtype)
+        for offs, nbytes, fmask, addr in chunks:
+            raw = bytes(self.buf[self.at(addr):self.at(addr) + nbytes])
             for k, (fid, _) in reversed(list(enumerate(filters))):
                 if fmask >> k & 1:
                     continue
@@ -538,7 +544,8 @@ class _Reader:
             q += r8(dt_size)
             shape, _ = self.shape_of(body[q:q + ds_size]) if ds_size >= 8 and body[q + 1] else ((), None)
             q += r8(ds_size)
-            out[name] = self.decode(dtype, shape, body[q:])
+            v = self.decode(dtype, shape, body[q:])
+            out[name] = v.copy() if isinstance(v, np.ndarray) else v
         return out
 
     def group(self, header_addr):
@@ -560,7 +567,8 @@ class _Reader:
 
 
 def read(path):
-    """{dataset name: array, sub-group name: dict, "attrs": {...}} of the root group."""
+    """{dataset name: array, sub-group name: dict, "attrs": {...}} of the root group.  Uncompressed datasets come back
+    as read-only views of the memory-mapped file (like the raw container's memmap): nothing is copied until it is used."""
     r = _Reader(path)
     return r.group(r.root_header)
 

@@ -92,6 +92,13 @@ def reduce_max_velocity(dist, local_max, device=None):
     return float("nan") if t[1].item() > 0 else float(t[0].item())
 
 
+class _DeviceArray:
+    """A raw device pointer as `__cuda_array_interface__`, so that torch.distributed can send it (no copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
 class SlabLBM:
     """`LBM2D_MRT_LES` for one slab of a decomposed domain: same methods; `get_force` / `get_max_velocity`
     return GLOBAL values on every rank, field getters return this rank's owned columns
@@ -102,7 +109,7 @@ class SlabLBM:
         if dist is None:
             import torch.distributed as dist
         self.dist, self.rank, self.world = dist, rank, world
-        self._pin_rings = {}
+        self._pin_rings, self._gather_states = {}, {}
         nx = config["simulation"]["nx"]
         self.slabs = partition(nx, world)
         self.x0, self.nx_owned = self.slabs[rank]
@@ -196,6 +203,54 @@ class SlabLBM:
     def export_stats(self):
         return self.solver.export_stats()
 
+    def export_frame_gathered(self):
+        """One export frame assembled on rank 0 (None elsewhere).  Over NCCL the ranks' column ranges never touch their
+        own hosts: the frame stays on the GPU (`lbm_export_frame_device`), is gathered GPU to GPU into a buffer that
+        was sized once, and only rank 0 copies the whole frame to (page-locked) host memory."""
+        if self.world == 1 or self._device is None:
+            return self.gather_columns(self.solver.export_frame())
+        import torch
+
+        ptr, shape = self.solver.export_frame_device()
+        st = self._gather_state(shape, torch)
+        if shape[-1]:
+            local = torch.as_tensor(_DeviceArray(ptr, shape), device=self._device)
+            st["pad"][..., :shape[-1]].copy_(local)
+            torch.cuda.current_stream().synchronize()   # the handle's frame buffer is free for the next export
+        self.dist.gather(st["pad"], st["parts"], dst=0)
+        if self.rank != 0:
+            return None
+        torch.cat([p[..., :w] for p, w in zip(st["parts"], st["widths"])], dim=-1, out=st["full"])
+        return self._to_pinned(st["full"], torch)
+
+    def _gather_state(self, shape, torch):
+        key = tuple(shape[:-1])
+        st = self._gather_states.get(key)
+        if st is None:   # once per export geometry: widths of all ranks, the padded send buffer, rank 0's receive buffers
+            w = torch.zeros(self.world, dtype=torch.int64, device=self._device)
+            w[self.rank] = shape[-1]
+            self.dist.all_reduce(w)
+            widths = [int(v) for v in w.tolist()]
+            wmax = max(max(widths), 1)
+            pad = torch.zeros(key + (wmax,), dtype=torch.float32, device=self._device)
+            parts = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
+            full = torch.empty(key + (sum(widths),), dtype=torch.float32, device=self._device) if self.rank == 0 else None
+            st = self._gather_states[key] = {"widths": widths, "pad": pad, "parts": parts, "full": full}
+        return st
+
+    def _to_pinned(self, full, torch):
+        """One D2H copy into page-locked memory (a pageable destination runs at ~4 GB/s: 25 ms for the 86 MB frame of 8
+        slabs).  The frame is handed to the writer thread, whose queue holds at most 5: a ring of 7 buffers is never
+        overwritten while in use (5 queued + 1 being written + the one being filled)."""
+        key = (tuple(full.shape), full.dtype)
+        ring = self._pin_rings.get(key)
+        if ring is None:   # page-locking is slow (~20 ms per buffer): all seven at the first frame, i.e. during start-up
+            ring = self._pin_rings[key] = {"bufs": [torch.empty(full.shape, dtype=full.dtype, pin_memory=True) for _ in range(7)], "next": 0}
+        host = ring["bufs"][ring["next"] % 7]
+        ring["next"] += 1
+        host.copy_(full)
+        return host.numpy()
+
     def gather_columns(self, local):
         """Concatenate per-rank arrays along their LAST axis (output columns) on rank 0 (None elsewhere).
         Over NCCL the arrays travel as tensors padded to the widest rank (one collective, no pickling)."""
@@ -220,18 +275,7 @@ class SlabLBM:
         self.dist.gather(pad, parts, dst=0)
         if self.rank != 0:
             return None
-        full = torch.cat([p[..., :w] for p, w in zip(parts, widths)], dim=-1)
-        # one D2H copy into page-locked memory (a pageable destination runs at ~4 GB/s: 25 ms for the 86 MB frame of 8
-        # slabs).  The frame is handed to the writer thread, whose queue holds at most 5: a ring of 7 buffers is never
-        # overwritten while in use (5 queued + 1 being written + the one being filled).
-        key = (tuple(full.shape), full.dtype)
-        ring = self._pin_rings.get(key)
-        if ring is None:   # page-locking is slow (~20 ms per buffer): all seven at the first frame, i.e. during start-up
-            ring = self._pin_rings[key] = {"bufs": [torch.empty(full.shape, dtype=full.dtype, pin_memory=True) for _ in range(7)], "next": 0}
-        host = ring["bufs"][ring["next"] % 7]
-        ring["next"] += 1
-        host.copy_(full)
-        return host.numpy()
+        return self._to_pinned(torch.cat([p[..., :w] for p, w in zip(parts, widths)], dim=-1), torch)
 
     def gather(self, local):
         """Concatenate per-rank owned-column arrays along x on rank 0 (None elsewhere)."""

@@ -238,6 +238,12 @@ class LBM2D_MRT_LES:
         _capi.check(self._lib.lbm_export_frame(self._h, out.ctypes.data_as(C.c_void_p) if want_frame else None))
         return out
 
+    def export_frame_device(self):
+        """The same frame left on the GPU: (device pointer or None, shape).  Valid until the next export call."""
+        ptr = C.c_void_p()
+        _capi.check(self._lib.lbm_export_frame_device(self._h, C.byref(ptr)))
+        return ptr.value, self._export_shape
+
     def export_stats(self):
         """Running accumulators of io/lbm_writer.py:176-210 -> dict (float64 arrays) + count."""
         c, h, w = self._export_shape

@@ -152,6 +152,10 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg);
  * the concatenation over ranks is the single-GPU / cv2 result.  lbm_export_frame() then fills (9, target_h, dhi-dlo). */
 int lbm_export_layout(LbmHandle h, int32_t *dlo, int32_t *dhi, int32_t *target_h);
 int lbm_export_frame(LbmHandle h, float *out_chw);
+/* The same frame left on the device: *frame_chw_dev points at the handle's (9, target_h, dhi-dlo) float32 buffer (NULL
+ * when this rank holds no output column), complete when the call returns and valid until the next export call.  For the
+ * x-slab writer: the ranks' column ranges are gathered GPU to GPU (NCCL) and only rank 0 copies the frame to the host. */
+int lbm_export_frame_device(LbmHandle h, const float **frame_chw_dev);
 int lbm_export_stats(LbmHandle h, double *running_sum_chw, double *vel_sq_sum_hw, double *abs_vor_sum_hw,
                      double *min9, double *max9, int64_t *count);
 

@@ -16,9 +16,8 @@ for it in range(3):
     s.synchronize(); t.append(time.perf_counter())
     f = s.get_force(); t.append(time.perf_counter())
     v = s.get_max_velocity(); t.append(time.perf_counter())
-    fr = s.export_frame(); t.append(time.perf_counter())
-    g = s.gather_columns(fr); t.append(time.perf_counter())
+    g = s.export_frame_gathered(); t.append(time.perf_counter())
     if rank == 0:
-        names = ["enqueue run_step(500)", "gpu wait", "get_force", "get_max_velocity", "export_frame", "gather_columns"]
+        names = ["enqueue run_step(500)", "gpu wait", "get_force", "get_max_velocity", "export_frame_gathered"]
         print(it, {n: round((b - a) * 1e3, 2) for n, a, b in zip(names, t, t[1:])}, flush=True)
 w.close(); s.close(); dist.destroy_process_group()

@@ -51,8 +51,8 @@ def test_writer_emits_the_bytes_libhdf5_emits_for_the_same_content():
     mine = h5._attribute_message("MATLAB_class", struct.pack("<BBBBI", 0x13, 0, 0, 0, 6), h5._space_message(()), b"double")
     assert mine[8:8 + len(attr)].rstrip(b"\0") == attr.rstrip(b"\0")            # version-1 attribute with a scalar dataspace
     p = r.at(header)
-    assert r.buf[p:p + 2] == h5._object_header([])[:2] and r.buf[p + 12:p + 16] == b"\0" * 4   # 16-byte version-1 prefix
-    sb = r.buf[512:512 + 96]
+    assert bytes(r.buf[p:p + 2]) == h5._object_header([])[:2] and bytes(r.buf[p + 12:p + 16]) == b"\0" * 4   # 16-byte version-1 prefix
+    sb = bytes(r.buf[512:512 + 96])
     mine = h5.Writer._superblock(0x60, 0x180, 0x260, 4168)
     assert mine[:20] == sb[:20] and mine[32:40] == sb[32:40] and mine[48:56] == sb[48:56]   # versions, sizes, K values, UNDEFs
     assert struct.unpack_from("<II", sb, 72) == (1, 0) == struct.unpack_from("<II", mine, 72)   # root entry: cached group
@@ -110,7 +110,7 @@ def test_structure_of_the_extensible_dataset(tmp_path):
     lay = msgs[h5.MSG_LAYOUT]
     assert lay[0] == 3 and lay[1] == 2 and lay[2] == 5 and struct.unpack_from("<5I", lay, 11) == (1, 9, 4, 6, 4)
     root = r.at(struct.unpack_from("<Q", lay, 3)[0])
-    assert r.buf[root:root + 4] == b"TREE" and r.buf[root + 4] == 1 and r.buf[root + 5] == 1   # chunk tree, level 1
+    assert bytes(r.buf[root:root + 4]) == b"TREE" and r.buf[root + 4] == 1 and r.buf[root + 5] == 1   # chunk tree, level 1
     chunks = r.chunks(struct.unpack_from("<Q", lay, 3)[0], 5)
     assert [c[0] for c in chunks] == [(i, 0, 0, 0, 0) for i in range(130)]
     assert all(c[1] == 9 * 4 * 6 * 4 and c[2] == 0 and c[3] % 8 == 0 for c in chunks)
