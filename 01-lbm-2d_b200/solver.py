@@ -80,6 +80,7 @@ class _PinnedPool:
 
 class LBM2D_MRT_LES:
     _PIN_THRESHOLD = 64 << 20   # bytes: frames at least this large come from the pinned pool
+    _EXPORT_PIN_THRESHOLD = 1 << 20   # export frames (9, H, W) at least this large likewise
 
     def __init__(self, config, mask_data=None, *, arith="strict", kernel="auto", device=None, slab=None,
                  obstacle_mode="refill"):
@@ -141,6 +142,7 @@ class LBM2D_MRT_LES:
         _capi.check(self._lib.lbm_create(C.byref(p), mask_ptr, C.byref(h)))
         self._h = h
         self._pool = None
+        self._frame_pool = None
 
         # Taichi-field look-alikes (ref:99-128); only `.to_numpy()` is supported
         self.vel = _FieldShim(lambda: self._get("lbm_get_vel", (self._nx_owned, self.ny, 2)))
@@ -234,7 +236,14 @@ class LBM2D_MRT_LES:
 
     def export_frame(self, want_frame=True):
         """One export frame (9, H, W): moments -> crop -> INTER_AREA on the GPU, statistics accumulated there."""
-        out = np.empty(self._export_shape, np.float32) if want_frame else None
+        out = None
+        if want_frame:   # like get_moments_numpy(): a fresh caller-owned array (it is queued to the writer thread), pinned when large
+            if int(np.prod(self._export_shape)) * 4 >= self._EXPORT_PIN_THRESHOLD:
+                if self._frame_pool is None:
+                    self._frame_pool = _PinnedPool(self._lib, max_bytes=1 << 30)
+                out = self._frame_pool.take(self._export_shape)
+            if out is None:
+                out = np.empty(self._export_shape, np.float32)
         _capi.check(self._lib.lbm_export_frame(self._h, out.ctypes.data_as(C.c_void_p) if want_frame else None))
         return out
 
@@ -310,9 +319,11 @@ class LBM2D_MRT_LES:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.lbm_destroy(h)
-        pool, self._pool = getattr(self, "_pool", None), None
-        if pool is not None:
-            pool.close()
+        for name in ("_pool", "_frame_pool"):
+            pool = getattr(self, name, None)
+            setattr(self, name, None)
+            if pool is not None:
+                pool.close()
 
     def __del__(self):
         try:

@@ -104,3 +104,26 @@ def test_static_mask_and_sdf_on_the_device_match_cv2_and_scipy(pkg, nx, ny, roi,
     empty = pkg.LBM2D_MRT_LES(make_config(nx, ny), mask_data=np.zeros((nx, ny), bool))
     assert np.array_equal(empty.static_mask_fields(x0, x1, y0, y1, *target),
                           dw.static_mask_host(np.zeros((nx, ny), bool), x0, x1, y0, y1, *target))
+
+
+def test_large_export_frames_are_fresh_pinned_arrays(pkg):
+    """Export frames of a megabyte and more come from a page-locked pool (one DMA, no page faults) and are still fresh
+    caller-owned arrays: the writer thread keeps up to 5 queued, so two live frames never share memory, a dropped frame's
+    buffer is reused, and beyond the pool's 7 buffers the call falls back to pageable arrays."""
+    nx, ny = 1200, 400
+    cfg = make_config(nx, ny, rho_in=1.01, nu=0.02, warmup=10, sponge=(8, 32, 4, 4), buffer=0, save_h=196, compute_step_size=5)
+    s = pkg.LBM2D_MRT_LES(cfg, mask_data=cylinder_mask(nx, ny, 300, 200, 30), arith="strict")
+    s.init()
+    s.export_configure(8, nx - 32, 4, ny - 4, int((nx - 40) * (196 / (ny - 8))), 196)
+    assert int(np.prod(s._export_shape)) * 4 >= s._EXPORT_PIN_THRESHOLD
+    s.run_step(5)
+    ref = s.export_frame().copy()
+    live = [s.export_frame() for _ in range(9)]          # the solver state is unchanged: the same frame nine times
+    ptrs = [a.ctypes.data for a in live]
+    assert len(set(ptrs)) == 9 and all(np.array_equal(a, ref) for a in live)
+    first = ptrs[0]
+    del live[0]                                           # its buffer goes back to the pool ...
+    again = s.export_frame()
+    assert again.ctypes.data == first and np.array_equal(again, ref)   # ... and is what the next frame gets
+    s.close()
+    assert np.array_equal(again, ref)                     # frames outlive the solver
