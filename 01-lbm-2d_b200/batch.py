@@ -98,16 +98,23 @@ def _gpu_runner(name, cfg, mask, out_dir, device, max_steps, progress):
     pkg = importlib.import_module("01-lbm-2d_b200")
     ops = importlib.import_module("01-lbm-2d_b200.simulation_ops")
     dwm = importlib.import_module("01-lbm-2d_b200.device_writer")
+    t = [time.perf_counter()]
     solver = pkg.LBM2D_MRT_LES(cfg, mask_data=mask, device=device)
     try:
         solver.init()
+        t.append(time.perf_counter())
         writer = dwm.DeviceLBMCaseWriter(os.path.join(out_dir, f"{name}.h5"), cfg, solver.nx, solver.ny,
                                          mask_data=mask, solver=solver)
+        t.append(time.perf_counter())
         meta = ops.run_simulation_loop(cfg, solver, None, None, None, writer,
                                        max_steps or cfg["simulation"]["max_steps"], progress=progress)
+        t.append(time.perf_counter())
         writer.close()
+        t.append(time.perf_counter())
     finally:
         solver.close()
+    if os.environ.get("LBM2D_CASE_TIMING"):   # where a case's wall time goes (ms): create + init | writer + static mask | run loop | file close
+        print(f"[case {name}] " + " | ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(t, t[1:])), file=sys.stderr)
     return meta
 
 
@@ -232,6 +239,12 @@ def run_sweep(n_cases=64, out_dir="gpurun_out/sweep", max_steps=None, max_succes
     warm.init()
     warm.run_step(2)
     warm.get_max_velocity()
+    # a GPU that has been idle takes a second or two to leave its low-power clocks; a sweep runs for minutes to hours, so
+    # the cases/hour window starts on a GPU that is already busy (like process start-up, reported as excluded time)
+    t_busy = time.perf_counter()
+    while time.perf_counter() - t_busy < float(os.environ.get("LBM2D_SWEEP_WARM_S", "2.0")):
+        warm.run_step(2000)
+        warm.get_max_velocity()
     warm.close()
     startup_s = time.perf_counter() - t_start
     if rank == 0:

@@ -152,6 +152,41 @@ def static_mask_host(mask, x0, x1, y0, y1, target_w, target_h):
     return np.stack([small, sdf], axis=0).astype(np.float32)
 
 
+class _HostExport:
+    """The export reduction on the host, for what the device kernels do not cover: a target LARGER than the ROI
+    (`save_resolution_height` above the cropped height -- cv2's INTER_AREA then interpolates, a different algorithm from the
+    area average the device restates).  Same interface as the solver's export_* calls; the frame is what the reference
+    computes (writer:144-170, cv2 itself) from `get_moments_numpy()`, the statistics are writer:176-210."""
+
+    def __init__(self, solver, x0, x1, y0, y1, target_w, target_h, channels=9):
+        self.solver, self.roi, self.size, self.channels = solver, (slice(x0, x1), slice(y0, y1)), (target_w, target_h), channels
+        self.sum = np.zeros((channels, target_h, target_w), np.float64)
+        self.vel_sq = np.zeros((target_h, target_w), np.float64)
+        self.vor = np.zeros((target_h, target_w), np.float64)
+        self.count = 0
+        self.mn, self.mx = np.full(channels, np.inf), np.full(channels, -np.inf)
+
+    def export_frame(self, want_frame=True):
+        import cv2
+
+        hwc = self.solver.get_moments_numpy()[self.roi[0], self.roi[1], :].transpose(1, 0, 2)
+        frame = np.stack([cv2.resize(np.ascontiguousarray(hwc[:, :, i]), self.size, interpolation=cv2.INTER_AREA)
+                          for i in range(self.channels)], axis=0).astype(np.float32)
+        self.sum += frame
+        self.count += 1
+        self.mn = np.minimum(self.mn, frame.min(axis=(1, 2)))
+        self.mx = np.maximum(self.mx, frame.max(axis=(1, 2)))
+        rho_safe = np.maximum(frame[0], 1e-6)
+        u, v = frame[3] / rho_safe, frame[5] / rho_safe
+        self.vel_sq += u**2 + v**2
+        self.vor += np.abs(np.gradient(v, axis=1) - np.gradient(u, axis=0))
+        return frame
+
+    def export_stats(self):
+        return {"running_sum": self.sum, "running_vel_sq_sum": self.vel_sq, "sum_abs_vor": self.vor, "global_min": self.mn,
+                "global_max": self.mx, "running_count": self.count}
+
+
 class _AsyncAppender:
     """File writes off the solver thread, as the reference's AsyncLBMCaseWriter does (writer:260-296): a bounded
     queue (depth 5) feeds one worker thread that appends to the container; `drain()` joins it."""
@@ -207,6 +242,7 @@ class DeviceLBMCaseWriter:
         self.n_frames = 0
         self.last_frame = None
         self._solver = None
+        self._host_export = None
         self._mask = None if mask_data is None else np.asarray(mask_data)
         self._container_kind = self._pick_container(container)
         self._container = None
@@ -253,7 +289,13 @@ class DeviceLBMCaseWriter:
             self._appender = _AsyncAppender(self._container)
 
     def attach(self, solver):
-        solver.export_configure(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
+        self._host_export = None
+        if (self.target_h > self.crop_h or self.target_w > self.crop_w) and getattr(solver, "world", 1) == 1 \
+                and hasattr(solver, "get_moments_numpy"):
+            # up-sampling target: the device reduction covers INTER_AREA shrinking only -> the reference's host path
+            self._host_export = _HostExport(solver, self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h, self.channels)
+        else:
+            solver.export_configure(self.x0, self.x1, self.y0, self.y1, self.target_w, self.target_h)
         self._solver = solver
         self._open()
 
@@ -266,7 +308,7 @@ class DeviceLBMCaseWriter:
         if getattr(sv, "world", 1) > 1:   # x-slabs: every rank holds a column range of the frame; rank 0 writes
             frame = sv.export_frame_gathered() if hasattr(sv, "export_frame_gathered") else sv.gather_columns(sv.export_frame())
         else:
-            frame = sv.export_frame()
+            frame = (self._host_export or sv).export_frame()
         if self._container is not None:
             self._appender.append(frame)   # the frame is a fresh array: the worker thread owns it from here
         self.last_frame = frame
@@ -287,7 +329,7 @@ class DeviceLBMCaseWriter:
             return None
         self.is_closed = True
         sv = self._solver
-        st = sv.export_stats() if sv is not None else {"running_count": 0}
+        st = (self._host_export or sv).export_stats() if sv is not None else {"running_count": 0}
         if self._container is None and getattr(sv, "world", 1) == 1:
             self._open()
         if getattr(sv, "world", 1) > 1:
@@ -306,7 +348,8 @@ class DeviceLBMCaseWriter:
                        sum_vor=st["sum_abs_vor"].astype(np.float32))
             meta = dict(self.config)
             meta["_dataset_info"] = {"original_crop": [self.crop_w, self.crop_h], "saved_resolution": [self.target_w, self.target_h],
-                                     "resize_algo": "INTER_AREA (per channel, on device)"}
+                                     "resize_algo": "cv2.INTER_AREA (per channel, host)" if self._host_export
+                                     else "INTER_AREA (per channel, on device)"}
             attrs = {"config_json": json.dumps(meta, default=str), "stats_min": st["global_min"], "stats_max": st["global_max"],
                      "stats_mean": np.mean(mean_field, axis=(1, 2))}
         self.attrs = attrs

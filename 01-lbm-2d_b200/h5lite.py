@@ -214,7 +214,7 @@ class Writer:
             _, shape, dtype, addr, nbytes = d
             space = _space_message(shape)
             layout = struct.pack("<BB", 3, 1) + struct.pack("<QQ", addr, nbytes)
-            fill = struct.pack("<BBBB", 2, 2, 2, 0)          # allocate late, write the fill value if set, none defined
+            fill = struct.pack("<BBBBI", 2, 2, 2, 1, 0)      # allocate late, fill if set, the default (zero) fill value
         else:
             ap = d[1]
             dtype = ap.dtype
@@ -222,7 +222,7 @@ class Writer:
             dims = (1,) + ap.frame_shape + (dtype.itemsize,)
             layout = struct.pack("<BBB", 3, 2, len(dims)) + struct.pack("<Q", self._chunk_index(ap)) + \
                 b"".join(struct.pack("<I", v) for v in dims)
-            fill = struct.pack("<BBBB", 2, 3, 2, 0)          # allocate incrementally
+            fill = struct.pack("<BBBBI", 2, 3, 2, 1, 0)      # allocate incrementally
         return _object_header([_message(MSG_DATASPACE, space), _message(MSG_DATATYPE, _dt_message(dtype), 1),
                                _message(MSG_FILL, fill), _message(MSG_LAYOUT, layout)])
 

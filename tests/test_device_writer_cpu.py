@@ -2,6 +2,7 @@
 and the explicitly named raw container), streaming (one frame in memory, frames on disk before finalize), the dataset /
 attribute set of the reference writer (io/lbm_writer.py:69-133, 212-251), and the VALUES of `static_mask` (row a19)."""
 import importlib
+import json
 import os
 
 import numpy as np
@@ -120,3 +121,37 @@ def test_static_mask_values_row_a19():
     assert np.array_equal(sm[1], sdf.astype(np.float32))
     assert (sm[1][~solid] > 0).all() and (sm[1][solid] < 0).all()
     assert sm[1][solid].min() <= -6 and abs(sm[1][0, 0] - np.hypot(*np.argwhere(solid).min(axis=0))) < 12   # deep inside / far away
+
+
+def test_upsampling_target_takes_the_reference_host_path(tmp_path):
+    """`save_resolution_height` above the ROI height: the device reduction covers INTER_AREA shrinking only, so the writer
+    computes such frames the way the reference does (cv2 on get_moments_numpy()) instead of refusing the config."""
+    import cv2
+
+    nx, ny = 64, 40
+    cfg = make_config(nx, ny, sponge=(4, 8, 2, 2), buffer=1, save_h=50)      # ROI 51 x 34 -> target 75 x 50
+
+    class MomentSolver:
+        def __init__(self):
+            self.n = 0
+
+        def export_configure(self, *a):
+            raise AssertionError("the device reduction must not be asked to up-sample")
+
+        def get_moments_numpy(self):
+            self.n += 1
+            rng = np.random.default_rng(self.n)
+            m = rng.standard_normal((nx, ny, 9)).astype(np.float32) * 0.01
+            m[..., 0] += 1.0
+            return m
+
+    w = dw.DeviceLBMCaseWriter(str(tmp_path / "up.h5"), cfg, nx, ny, solver=MomentSolver(), container="h5lite")
+    assert (w.target_w, w.target_h) == (75, 50) and w.target_h > w.crop_h
+    for _ in range(3):
+        w.append_from_solver()
+    out = w.finalize()
+    m1 = MomentSolver().get_moments_numpy()
+    want = cv2.resize(np.ascontiguousarray(m1[4:55, 3:37, 3].T), (75, 50), interpolation=cv2.INTER_AREA)
+    assert out["turbulence"].shape == (3, 9, 50, 75) and np.array_equal(out["turbulence"][0, 3], want)
+    assert np.array_equal(out["mean_vel_field"], (np.asarray(out["turbulence"], np.float64).sum(axis=0) / 3).astype(np.float32))
+    assert json.loads(out["attrs"]["config_json"])["_dataset_info"]["resize_algo"].endswith("host)")
