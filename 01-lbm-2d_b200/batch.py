@@ -198,11 +198,20 @@ def run_cases(cases, out_dir, rank=0, world=1, device=None, max_steps=None, prog
                 cond.notify_all()
 
     threads = [threading.Thread(target=worker, name=f"lbm-case-{i}") for i in range(max(1, int(concurrency)) - 1)]
-    for t in threads:
-        t.start()
-    worker()
-    for t in threads:
-        t.join()
+    # A batch of a sweep case is ~1 ms of GPU work and a handful of short Python steps between blocking C calls; with
+    # the interpreter's default 5 ms switch interval a case thread coming back from such a call can wait that long for
+    # the lock while another thread runs Python code (frame bookkeeping, file metadata) -- several batches' worth.
+    old_interval = sys.getswitchinterval()
+    if threads:
+        sys.setswitchinterval(min(old_interval, 2e-4))
+    try:
+        for t in threads:
+            t.start()
+        worker()
+        for t in threads:
+            t.join()
+    finally:
+        sys.setswitchinterval(old_interval)
     with cond:
         flush()
     return results

@@ -10,10 +10,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <sys/mman.h>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "lbm2d_export.cuh"
@@ -76,6 +78,78 @@ inline Api &api() {
 }
 }  // namespace nccl
 
+// Device memory of destroyed single-GPU handles is kept for the next handle of the process.  A dataset sweep creates and
+// destroys a solver per case, several at a time on one GPU (batch.py): ~30 cudaMalloc and, worse, ~30 cudaFree per case --
+// and cudaFree synchronises the whole device, i.e. it stalls the steps of the OTHER cases in flight.  Blocks are recycled
+// whole (never sub-allocated), zeroed on reuse (what fresh cudaMalloc memory is in practice), capped in size and total;
+// x-slab handles (their buffers are exported through CUDA IPC and may be large) keep plain cudaMalloc / cudaFree.
+namespace devpool {
+constexpr size_t kMaxBlock = (size_t)64 << 20, kMaxCached = (size_t)1 << 30;
+struct Pool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;
+    std::unordered_map<void *, std::pair<int, size_t>> live;
+    size_t cached = 0;
+};
+inline Pool &pool() {
+    static Pool *p = new Pool;   // never destroyed: the CUDA context may be gone by the time static destructors run
+    return *p;
+}
+inline bool enabled() {
+    static const bool on = !std::getenv("LBM2D_NO_POOL");
+    return on;
+}
+inline cudaError_t alloc(void **ptr, size_t bytes, bool pooled) {
+    const size_t sz = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    if (!pooled || !enabled() || sz > kMaxBlock) return cudaMalloc(ptr, bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Pool &p = pool();
+    void *q = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(p.mu);
+        auto it = p.free_blocks.find({dev, sz});
+        if (it != p.free_blocks.end()) {
+            q = it->second;
+            p.free_blocks.erase(it);
+            p.cached -= sz;
+        }
+    }
+    if (q) {   // its previous owner synchronised its stream before giving it back (lbm_destroy)
+        cudaError_t e = cudaMemsetAsync(q, 0, sz, cudaStreamLegacy);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // the handle's own stream is non-blocking: order by hand
+        if (e != cudaSuccess) return e;
+    } else {
+        cudaError_t e = cudaMalloc(&q, sz);
+        if (e != cudaSuccess) return e;
+    }
+    {
+        std::lock_guard<std::mutex> lk(p.mu);
+        p.live[q] = {dev, sz};
+    }
+    *ptr = q;
+    return cudaSuccess;
+}
+inline void release(void *ptr) {
+    if (!ptr) return;
+    Pool &p = pool();
+    {
+        std::lock_guard<std::mutex> lk(p.mu);
+        auto it = p.live.find(ptr);
+        if (it != p.live.end()) {
+            const auto key = it->second;
+            p.live.erase(it);
+            if (p.cached + key.second <= kMaxCached) {
+                p.free_blocks.emplace(key, ptr);
+                p.cached += key.second;
+                return;
+            }
+        }
+    }
+    cudaFree(ptr);
+}
+}  // namespace devpool
+
 struct LbmSolver {
     LbmParams p{};
     nccl::Comm comm = nullptr;
@@ -116,6 +190,8 @@ struct LbmSolver {
     bool use_graph = true;
     int graph_min_steps = 8;
     std::map<long long, cudaGraphExec_t> graphs;
+    bool pooled = false;                  // device memory through devpool (single-GPU handles)
+    template <class T> cudaError_t dalloc(T **ptr, size_t bytes) { return devpool::alloc((void **)ptr, bytes, pooled); }
     unsigned long long *progress = nullptr;   // device counter, see step_kernel
     unsigned long long progress_total = 0;    // its value once every step launched so far has signalled
     int tma_grid = 0;
@@ -161,7 +237,7 @@ struct LbmSolver {
                           (void *)exp_xoff, (void *)exp_yoff, (void *)exp_tmp, (void *)exp_frame, (void *)exp_sum,
                           (void *)exp_velsq, (void *)exp_vor, (void *)exp_minmax, (void *)exp_halo, (void *)exp_ecount,
                           (void *)progress, (void *)code_bits, (void *)links8, (void *)inbox})
-            if (ptr) cudaFree(ptr);
+            if (ptr) devpool::release(ptr);
         for (int i = 0; i < 2; ++i) {
             if (pinned[i]) cudaFreeHost(pinned[i]);
             if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
@@ -176,10 +252,10 @@ constexpr int kForceBlocks = 128;
 
 int ensure_staging(LbmSolver *s, size_t floats) {
     if (s->staging_floats >= floats) return LBM_OK;
-    if (s->staging) cudaFree(s->staging);
+    if (s->staging) devpool::release(s->staging);
     s->staging = nullptr;
     s->staging_floats = 0;
-    CUDA_TRY(cudaMalloc(&s->staging, floats * sizeof(float)));
+    CUDA_TRY(s->dalloc(&s->staging, floats * sizeof(float)));
     s->staging_floats = floats;
     return LBM_OK;
 }
@@ -582,28 +658,29 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
     } while (0)
 
     CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->pooled = p.nx == p.nx_global;   // x-slabs export their buffers through CUDA IPC: plain allocations
     const size_t fbytes = ((size_t)9 * s->plane + 64) * sizeof(float);  // +64: the last segment may prefetch past the end
-    CREATE_TRY(cudaMalloc(&s->f[0], fbytes));
-    CREATE_TRY(cudaMalloc(&s->f[1], fbytes));
+    CREATE_TRY(s->dalloc(&s->f[0], fbytes));
+    CREATE_TRY(s->dalloc(&s->f[1], fbytes));
     CREATE_TRY(cudaMemset(s->f[0], 0, fbytes));
     CREATE_TRY(cudaMemset(s->f[1], 0, fbytes));
-    CREATE_TRY(cudaMalloc(&s->mac, (size_t)3 * s->plane * sizeof(float)));
+    CREATE_TRY(s->dalloc(&s->mac, (size_t)3 * s->plane * sizeof(float)));
     s->rho = s->mac;
     s->ux = s->mac + s->plane;
     s->uy = s->mac + 2 * s->plane;
-    CREATE_TRY(cudaMalloc(&s->ring_ctx, 2 * sizeof(lbm::RingCtx)));
-    CREATE_TRY(cudaMalloc(&s->code, (size_t)s->plane + 64));
-    CREATE_TRY(cudaMalloc(&s->damp_x, s->nx_local * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&s->damp_y, s->pitch * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&s->ramp_tab, ((size_t)p.warmup_steps + 1) * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&s->ctr, 2 * sizeof(int)));
-    CREATE_TRY(cudaMalloc(&s->progress, sizeof(unsigned long long)));
+    CREATE_TRY(s->dalloc(&s->ring_ctx, 2 * sizeof(lbm::RingCtx)));
+    CREATE_TRY(s->dalloc(&s->code, (size_t)s->plane + 64));
+    CREATE_TRY(s->dalloc(&s->damp_x, s->nx_local * sizeof(float)));
+    CREATE_TRY(s->dalloc(&s->damp_y, s->pitch * sizeof(float)));
+    CREATE_TRY(s->dalloc(&s->ramp_tab, ((size_t)p.warmup_steps + 1) * sizeof(float)));
+    CREATE_TRY(s->dalloc(&s->ctr, 2 * sizeof(int)));
+    CREATE_TRY(s->dalloc(&s->progress, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(s->progress, 0, sizeof(unsigned long long)));
-    CREATE_TRY(cudaMalloc(&s->maxv, 2 * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&s->inbox, 4 * sizeof(unsigned long long)));
+    CREATE_TRY(s->dalloc(&s->maxv, 2 * sizeof(unsigned)));
+    CREATE_TRY(s->dalloc(&s->inbox, 4 * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(s->inbox, 0, 4 * sizeof(unsigned long long)));
-    CREATE_TRY(cudaMalloc(&s->force_partial, kForceBlocks * 2 * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&s->force_out, 2 * sizeof(float)));
+    CREATE_TRY(s->dalloc(&s->force_partial, kForceBlocks * 2 * sizeof(double)));
+    CREATE_TRY(s->dalloc(&s->force_out, 2 * sizeof(float)));
 
     // cell codes (bit0 = solid), padded to the pitch
     std::vector<uint8_t> code((size_t)s->plane + 64, 0);
@@ -623,14 +700,14 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
                     if (code[(size_t)(il - ex[k]) * s->pitch + (j - ey[k])] & 1) l |= (uint8_t)(1u << (k - 1));
                 links[o] = l;
             }
-        CREATE_TRY(cudaMalloc(&s->links8, links.size()));
+        CREATE_TRY(s->dalloc(&s->links8, links.size()));
         CREATE_TRY(cudaMemcpy(s->links8, links.data(), links.size(), cudaMemcpyHostToDevice));
     }
     {   // bit-packed copy for the interior warps (1/8 of the bytes per step)
         std::vector<uint32_t> bits(((size_t)s->plane + 31) / 32 + 2, 0u);
         for (size_t o = 0; o < (size_t)s->plane; ++o)
             if (code[o] & 1) bits[o >> 5] |= 1u << (o & 31);
-        CREATE_TRY(cudaMalloc(&s->code_bits, bits.size() * sizeof(uint32_t)));
+        CREATE_TRY(s->dalloc(&s->code_bits, bits.size() * sizeof(uint32_t)));
         CREATE_TRY(cudaMemcpy(s->code_bits, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
 
@@ -674,7 +751,7 @@ int lbm_create(const LbmParams *params, const uint8_t *mask_xy, LbmHandle *out) 
             return fail(LBM_ERR_INVALID, "slab too large for 32-bit link offsets");
         }
         if (s->n_links) {
-            CREATE_TRY(cudaMalloc(&s->links, links.size() * sizeof(lbm::Link)));
+            CREATE_TRY(s->dalloc(&s->links, links.size() * sizeof(lbm::Link)));
             CREATE_TRY(cudaMemcpy(s->links, links.data(), links.size() * sizeof(lbm::Link), cudaMemcpyHostToDevice));
         }
     }
@@ -1230,7 +1307,7 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     for (void **ptr : {(void **)&h->exp_xtab, (void **)&h->exp_ytab, (void **)&h->exp_xoff, (void **)&h->exp_yoff, (void **)&h->exp_tmp,
                        (void **)&h->exp_frame, (void **)&h->exp_sum, (void **)&h->exp_velsq, (void **)&h->exp_vor,
                        (void **)&h->exp_minmax, (void **)&h->exp_halo, (void **)&h->exp_ecount}) {
-        if (*ptr) cudaFree(*ptr);
+        if (*ptr) devpool::release(*ptr);
         *ptr = nullptr;
     }
     h->exp_ready = false;
@@ -1264,7 +1341,7 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     int e_recv = 0;
     if (dhi > dlo) e_recv = std::max(0, X0 + xt[xo[dhi] - 1].si - (rx1 - 1));
     int e_send = 0;
-    CUDA_TRY(cudaMalloc(&h->exp_ecount, 2 * sizeof(int)));
+    CUDA_TRY(h->dalloc(&h->exp_ecount, 2 * sizeof(int)));
     if (slabs) {  // tell the east neighbour how many of its first ROI columns this rank needs
         nccl::Api &n = nccl::api();
         CUDA_TRY(cudaMemcpyAsync(h->exp_ecount, &e_recv, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1284,17 +1361,17 @@ int lbm_export_configure(LbmHandle h, const LbmExportConfig *cfg) {
     g.cw = g.own_cols + e_recv;
 
     const size_t npx = (size_t)std::max(1, dhi - dlo) * g.th;
-    CUDA_TRY(cudaMalloc(&h->exp_xtab, xt.size() * sizeof(lbm::AreaEntry)));
-    CUDA_TRY(cudaMalloc(&h->exp_ytab, yt.size() * sizeof(lbm::AreaEntry)));
-    CUDA_TRY(cudaMalloc(&h->exp_xoff, xo.size() * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&h->exp_yoff, yo.size() * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&h->exp_tmp, (size_t)9 * std::max(1, g.cw) * ch * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&h->exp_frame, 9 * npx * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&h->exp_sum, 9 * npx * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->exp_velsq, npx * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->exp_vor, npx * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->exp_minmax, 18 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->exp_halo, (size_t)4 * 3 * g.th * sizeof(float)));
+    CUDA_TRY(h->dalloc(&h->exp_xtab, xt.size() * sizeof(lbm::AreaEntry)));
+    CUDA_TRY(h->dalloc(&h->exp_ytab, yt.size() * sizeof(lbm::AreaEntry)));
+    CUDA_TRY(h->dalloc(&h->exp_xoff, xo.size() * sizeof(int)));
+    CUDA_TRY(h->dalloc(&h->exp_yoff, yo.size() * sizeof(int)));
+    CUDA_TRY(h->dalloc(&h->exp_tmp, (size_t)9 * std::max(1, g.cw) * ch * sizeof(float)));
+    CUDA_TRY(h->dalloc(&h->exp_frame, 9 * npx * sizeof(float)));
+    CUDA_TRY(h->dalloc(&h->exp_sum, 9 * npx * sizeof(double)));
+    CUDA_TRY(h->dalloc(&h->exp_velsq, npx * sizeof(double)));
+    CUDA_TRY(h->dalloc(&h->exp_vor, npx * sizeof(double)));
+    CUDA_TRY(h->dalloc(&h->exp_minmax, 18 * sizeof(double)));
+    CUDA_TRY(h->dalloc(&h->exp_halo, (size_t)4 * 3 * g.th * sizeof(float)));
     CUDA_TRY(cudaMemcpy(h->exp_xtab, xt.data(), xt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->exp_ytab, yt.data(), yt.size() * sizeof(lbm::AreaEntry), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->exp_xoff, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
