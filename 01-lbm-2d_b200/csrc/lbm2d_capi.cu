@@ -1066,6 +1066,10 @@ int lbm_run(LbmHandle h, int steps) {
         const long long key = (long long)steps * 2 + (long long)(h->steps_done & 1);
         auto hit = h->graphs.find(key);
         if (hit == h->graphs.end()) {
+            if (h->graphs.size() >= 8) {   // a run loop uses one or two batch sizes; a caller cycling through many must not pile up graphs
+                for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+                h->graphs.clear();
+            }
             // thread-local capture: other cases (threads) of the same process keep allocating / launching meanwhile
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             const int64_t done0 = h->steps_done, total0 = h->steps_total, launches0 = h->launches;
