@@ -76,7 +76,7 @@ class _H5LiteContainer:
         self.w = h5lite.Writer(path)
         if static_mask is not None:
             self.w.create_dataset("static_mask", static_mask, "f4")
-        self.dset = self.w.create_appendable("turbulence", (channels, th, tw), "f4")
+        self.dset = self.w.create_appendable("turbulence", (channels, th, tw), "f4", gzip=4 if compression == "gzip" else None)
 
     def append(self, frame):
         self.dset.append(frame)

@@ -13,8 +13,9 @@ every libhdf5 since 1.6 -- and therefore h5py, h5dump, MATLAB, netCDF-4 -- opens
 * root attributes: numeric arrays (`stats_min/max/mean`) and variable-length UTF-8 strings (`config_json`, stored like
   h5py stores a Python str: a global-heap object).
 
-Not written: compression filters (the reference asks for `lzf`, an h5py-only plug-in filter; frames are stored
-uncompressed, which any reader handles), sub-groups, anything the case file does not use.
+Compression: `compression: gzip` (HDF5's standard deflate filter) is honoured per frame; the reference's default `lzf` is
+an h5py-only plug-in filter (id 32000, not part of HDF5), so such frames are stored uncompressed, which any reader
+handles.  Not written: sub-groups, anything the case file does not use.
 
 The reader (`read`) is written from the same specification and exists for `read_case()` on hosts without h5py and for the
 tests: it is pinned on a file produced by libhdf5 itself (a MATLAB 7.3 file shipped with scipy's test data), so the
@@ -91,17 +92,21 @@ def _attribute_message(name: str, dt: bytes, space: bytes, data: bytes) -> bytes
 
 
 class _Appendable:
-    def __init__(self, owner, name, frame_shape, dtype):
+    def __init__(self, owner, name, frame_shape, dtype, gzip=None):
         self.owner, self.name = owner, name
         self.frame_shape, self.dtype = tuple(int(d) for d in frame_shape), np.dtype(dtype)
         self.frame_bytes = int(np.prod(self.frame_shape)) * self.dtype.itemsize
-        self.addresses = []
+        self.gzip = None if gzip is None else int(gzip)    # deflate level: HDF5's standard filter 1
+        self.addresses, self.sizes = [], []
 
     def append(self, frame):
         a = np.ascontiguousarray(frame, self.dtype)
         if a.shape != self.frame_shape:
             raise ValueError(f"{self.name}: frame of shape {a.shape}, expected {self.frame_shape}")
+        if self.gzip is not None:
+            a = np.frombuffer(zlib.compress(a.tobytes(), self.gzip), np.uint8)
         self.addresses.append(self.owner._write_raw(a))
+        self.sizes.append(a.nbytes)
 
     def __len__(self):
         return len(self.addresses)
@@ -147,10 +152,11 @@ class Writer:
         _dt_message(a.dtype)
         self.datasets[name] = ("contiguous", a.shape, a.dtype, self._write_raw(a) if a.nbytes else UNDEF, a.nbytes)
 
-    def create_appendable(self, name, frame_shape, dtype="f4") -> _Appendable:
+    def create_appendable(self, name, frame_shape, dtype="f4", gzip=None) -> _Appendable:
+        """`gzip`: deflate level 0-9 per frame (the filter h5py calls compression="gzip"); None = stored as is."""
         self._check_name(name)
         _dt_message(np.dtype(dtype))
-        ap = _Appendable(self, name, frame_shape, dtype)
+        ap = _Appendable(self, name, frame_shape, dtype, gzip)
         self.datasets[name] = ("chunked", ap)
         return ap
 
@@ -186,7 +192,7 @@ class Writer:
 
         n = len(ap)
         # level 0: (first frame index, child address) per entry
-        entries = [(i, ap.addresses[i]) for i in range(n)]
+        entries = [(i, ap.addresses[i], ap.sizes[i]) for i in range(n)]
         level = 0
         while True:
             groups = [entries[i:i + 2 * CHUNK_K] for i in range(0, len(entries), 2 * CHUNK_K)] or [[]]
@@ -197,19 +203,19 @@ class Writer:
                 left = addrs[j - 1] if j > 0 else UNDEF
                 right = addrs[j + 1] if j + 1 < len(groups) else UNDEF
                 blob = b"TREE" + struct.pack("<BBH", 1, level, len(g)) + struct.pack("<QQ", left, right)
-                for first, child in g:
-                    blob += key(first, ap.frame_bytes) + struct.pack("<Q", child)
+                for first, child, nbytes in g:
+                    blob += key(first, nbytes) + struct.pack("<Q", child)
                 # the closing key: the first chunk of the next node, or one past the last frame
                 end = groups[j + 1][0][0] if j + 1 < len(groups) else n
-                blob += key(end, 0 if j + 1 == len(groups) else ap.frame_bytes)
+                blob += key(end, groups[j + 1][0][2] if j + 1 < len(groups) else 0)
                 self._write_meta(blob.ljust(node_size, b"\0"))
-                nxt.append((g[0][0] if g else 0, addrs[j]))
+                nxt.append((g[0][0] if g else 0, addrs[j], g[0][2] if g else 0))
             if len(nxt) == 1:
                 return nxt[0][1]
             entries, level = nxt, level + 1
 
     def _dataset_header(self, name) -> bytes:
-        d = self.datasets[name]
+        d, extra = self.datasets[name], []
         if d[0] == "contiguous":
             _, shape, dtype, addr, nbytes = d
             space = _space_message(shape)
@@ -223,8 +229,10 @@ class Writer:
             layout = struct.pack("<BBB", 3, 2, len(dims)) + struct.pack("<Q", self._chunk_index(ap)) + \
                 b"".join(struct.pack("<I", v) for v in dims)
             fill = struct.pack("<BBBBI", 2, 3, 2, 1, 0)      # allocate incrementally
+            if ap.gzip is not None:   # version-1 filter pipeline: one filter, id 1 (deflate), one client value (the level) + padding
+                extra = [_message(MSG_FILTERS, struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<I4x", ap.gzip), 1)]
         return _object_header([_message(MSG_DATASPACE, space), _message(MSG_DATATYPE, _dt_message(dtype), 1),
-                               _message(MSG_FILL, fill), _message(MSG_LAYOUT, layout)])
+                               _message(MSG_FILL, fill), _message(MSG_LAYOUT, layout)] + extra)
 
     def _attribute(self, name, value, strings) -> bytes:
         if isinstance(value, (str, bytes)):

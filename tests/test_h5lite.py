@@ -127,3 +127,29 @@ def test_rejects_what_it_cannot_store(tmp_path):
     with pytest.raises(ValueError):
         w.create_appendable("g/x", (2,))
     w.abort()
+
+
+def test_gzip_frames_use_the_standard_deflate_filter(tmp_path):
+    """`compression: gzip` in the case config: every frame is one deflate-compressed chunk, announced by a version-1
+    filter pipeline message (filter id 1) -- the layout h5py produces for compression="gzip"."""
+    import zlib
+
+    path = str(tmp_path / "z.h5")
+    w = h5.Writer(path)
+    dset = w.create_appendable("turbulence", (9, 8, 10), "f4", gzip=4)
+    frames = np.repeat(np.arange(70, dtype=np.float32), 9 * 8 * 10).reshape(70, 9, 8, 10)     # compressible
+    for f in frames:
+        dset.append(f)
+    w.close()
+    assert os.path.getsize(path) < frames.nbytes // 4
+    d = h5.read(path)
+    assert np.array_equal(d["turbulence"], frames)
+    r = h5._Reader(path)
+    (name, header), = [e for m in r.messages(r.root_header) if m[0] == h5.MSG_SYMTAB
+                      for e in r.group_entries(*struct.unpack_from("<QQ", m[2], 0))]
+    msgs = {t: body for t, _, body in r.messages(header)}
+    assert r.filters_of(msgs[h5.MSG_FILTERS]) == [(1, (4,))]
+    lay = msgs[h5.MSG_LAYOUT]
+    offs, nbytes, fmask, addr = r.chunks(struct.unpack_from("<Q", lay, 3)[0], 5)[69]
+    assert offs[0] == 69 and fmask == 0
+    assert zlib.decompress(bytes(r.buf[addr:addr + nbytes])) == frames[69].tobytes()
