@@ -61,6 +61,10 @@ class _PinnedPool:
         weakref.finalize(buf, self._give_back, ptr, nbytes)
         return np.ctypeslib.as_array(buf).reshape(shape)   # the array's base chain keeps `buf` alive
 
+    def free_count(self, shape):
+        with self._lock:
+            return len(self._free.get(int(np.prod(shape)) * 4, []))
+
     def _give_back(self, ptr, nbytes):
         with self._lock:
             if ptr in self._sizes:
@@ -233,14 +237,23 @@ class LBM2D_MRT_LES:
         _capi.check(self._lib.lbm_export_layout(self._h, C.byref(dlo), C.byref(dhi), C.byref(th)))
         self.export_columns = (int(dlo.value), int(dhi.value))   # this rank's columns of the global frame
         self._export_shape = (9, int(target_h), int(dhi.value - dlo.value))
+        if self._nx_owned == self.nx and self._pinned_frames():   # slabs gather their frames GPU to GPU (slab.py)
+            # page-locking is slow (~0.4 ms per MB): the first frames' buffers are made here, at set-up, not inside the run loop
+            held = [self._frame_pool.take(self._export_shape) for _ in range(3 - self._frame_pool.free_count(self._export_shape))]
+            del held
+
+    def _pinned_frames(self):
+        if int(np.prod(self._export_shape)) * 4 < self._EXPORT_PIN_THRESHOLD:
+            return False
+        if self._frame_pool is None:
+            self._frame_pool = _PinnedPool(self._lib, max_bytes=1 << 30)
+        return True
 
     def export_frame(self, want_frame=True):
         """One export frame (9, H, W): moments -> crop -> INTER_AREA on the GPU, statistics accumulated there."""
         out = None
         if want_frame:   # like get_moments_numpy(): a fresh caller-owned array (it is queued to the writer thread), pinned when large
-            if int(np.prod(self._export_shape)) * 4 >= self._EXPORT_PIN_THRESHOLD:
-                if self._frame_pool is None:
-                    self._frame_pool = _PinnedPool(self._lib, max_bytes=1 << 30)
+            if self._pinned_frames():
                 out = self._frame_pool.take(self._export_shape)
             if out is None:
                 out = np.empty(self._export_shape, np.float32)

@@ -102,7 +102,9 @@ int lbm_destroy(LbmHandle h);
 int lbm_init(LbmHandle h);
 
 /* run_step(steps), ref:552-573: `steps` fused collide+stream+macro+BC+refill passes.  Asynchronous.
- * The last pass of a call also materialises rho / vel and the max|u| reduction (ref:648-654). */
+ * The last pass of a call also materialises rho / vel and the max|u| reduction (ref:648-654).
+ * One kernel launch per step; on grids of less than ~2 waves of CTAs a whole call is replayed as one CUDA graph
+ * (captured once per `steps` value and buffer parity) once the soft-start ramp is over -- same results, one host call. */
 int lbm_run(LbmHandle h, int steps);
 int lbm_synchronize(LbmHandle h);
 
