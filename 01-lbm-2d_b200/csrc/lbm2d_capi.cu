@@ -351,8 +351,6 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.links8 = s->links8;
     a.damp_x = s->damp_x;
     a.damp_y = s->damp_y;
-    a.ctr_out = s->ctr + (par ^ 1);
-    a.frame = (int)(s->steps_done + 1);
     a.ramp = s->ramp_host[std::min<int64_t>(s->steps_done + 1, s->p.warmup_steps)];
     a.rho = s->rho;
     a.ux = s->ux;
@@ -370,7 +368,6 @@ lbm::StepArgs make_args(const LbmSolver *s, int par_override = -1) {
     a.il0 = 1;
     a.il_step = 1;
     a.il_count = s->nx_local - 2;
-    a.bump_ctr = 1;
     a.n_ring = lbm::ring_cell_count(a.il0, a.il_step, a.il_count, s->nx_local, s->ny, a.west_ring, a.east_ring);
     a.progress = s->progress;
     a.col_split = -1;
@@ -974,7 +971,7 @@ int lbm_run(LbmHandle h, int steps) {
     // instead of queueing on the context's launch lock.  The diagnostic step counter is set behind the graph.
     const bool graphable = h->use_graph && !h->use_tma && !(h->comm && h->nranks > 1) && !h->peer_mode && early_cols == 0 &&
                            steps >= h->graph_min_steps && h->steps_done + 1 >= (int64_t)h->p.warmup_steps;
-    auto enqueue = [&](bool in_graph) -> int {
+    auto enqueue = [&]() -> int {
     for (int it = 0; it < steps; ++it) {
         const bool emit = (it == steps - 1);
         if (emit) CUDA_TRY(cudaMemsetAsync(h->maxv, 0, 2 * sizeof(unsigned), h->stream));
@@ -1001,7 +998,6 @@ int lbm_run(LbmHandle h, int steps) {
             continue;
         }
         lbm::StepArgs a = make_args(h);
-        if (in_graph) { a.bump_ctr = 0; a.frame = 0; }   // nothing in a replayed node may depend on the step index
         if (col_split >= 0) { a.col_split = col_split; }
         else if (h->peer_mode) { a.col_split = ncols; }   // identity order il = 1 + col
         if (h->peer_mode) {   // grid rows of the edge columns: col -> row = groups of 33, shifted past the W/E ring block
@@ -1024,7 +1020,7 @@ int lbm_run(LbmHandle h, int steps) {
             // interior on the main stream meanwhile.  edge(n) needs interior(n-1) and exchange(n-1);
             // interior(n) needs edge(n-1) and interior(n-1); see DESIGN.md section 5 "slabs".
             lbm::StepArgs e = a;
-            e.il0 = 1; e.il_step = h->nx_local - 3; e.il_count = 2; e.bump_ctr = 0;
+            e.il0 = 1; e.il_step = h->nx_local - 3; e.il_count = 2;
             if (emit) CUDA_TRY(cudaEventRecord(h->ev_m, h->stream));  // orders the max|u| reset before the edge kernel
             CUDA_TRY(cudaStreamWaitEvent(h->stream_e, h->ev_m, 0));
             const dim3 eb = grid_for(e);
@@ -1061,7 +1057,7 @@ int lbm_run(LbmHandle h, int steps) {
     return LBM_OK;
     };
     if (!graphable) {
-        if (int rc = enqueue(false)) return rc;
+        if (int rc = enqueue()) return rc;
     } else {
         const long long key = (long long)steps * 2 + (long long)(h->steps_done & 1);
         auto hit = h->graphs.find(key);
@@ -1073,7 +1069,7 @@ int lbm_run(LbmHandle h, int steps) {
             // thread-local capture: other cases (threads) of the same process keep allocating / launching meanwhile
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             const int64_t done0 = h->steps_done, total0 = h->steps_total, launches0 = h->launches;
-            const int rc = enqueue(true);
+            const int rc = enqueue();
             cudaGraph_t graph = nullptr;
             const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             h->steps_done = done0; h->steps_total = total0; h->launches = launches0;   // nothing has run yet
@@ -1089,6 +1085,8 @@ int lbm_run(LbmHandle h, int steps) {
         h->steps_done += steps;
         h->steps_total += steps;
         h->launches += steps;
+    }
+    if (steps > 0 && !h->use_tma) {   // the diagnostic device copy of frame_count (the TMA kernel keeps its own)
         lbm::set_counter_kernel<<<1, 1, 0, h->stream>>>(h->ctr + (h->steps_done & 1), (int)h->steps_done);
         h->launches++;
     }

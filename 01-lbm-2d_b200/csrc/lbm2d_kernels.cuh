@@ -41,17 +41,14 @@ struct StepArgs {
     const uint32_t *__restrict__ code_bits;  // the same bit, 32 cells per word (plane order): what the interior warps read
     const float *__restrict__ damp_x;  // [nx_local]   ref:364-370 (indexed by local column, holds the global value)
     const float *__restrict__ damp_y;  // [pitch]      ref:372-378
-    int *ctr_out;                   // device copy of frame_count (diagnostic; the kernels use `frame` / `ramp`)
     float *rho, *ux, *uy;           // macroscopic planes (written by EMIT steps)
     unsigned *maxv_bits;            // max(ux^2+uy^2) as ordered uint; [1] = NaN flag
     long long plane;                // floats per plane = nx_local * pitch
     int nx_local, ny, pitch, nseg;
     int x_off;                      // global x of local column 0
     int west_ring, east_ring;       // local column 0 / nx_local-1 is the domain boundary (else a halo)
-    int frame;                      // frame_count after this step (ref:440), known on the host
     float ramp;                     // soft-start factor of this step, ref:442-443 (host table, see lbm2d_capi.cu)
     int il0, il_step, il_count;     // columns of this launch: il0 + blockIdx.y * il_step, blockIdx.y < il_count
-    int bump_ctr;                   // this launch advances frame_count (exactly one launch per step does)
     int n_ring;                     // ring cells handled by this launch's ring warps
     int ring_row0, ring_rows;       // grid rows [ring_row0, ring_row0 + ring_rows): W/E ring warps; the others: see step_kernel
     // Early start (see step_kernel): rows [0, early_rows) may begin on the progress counter instead of the full
@@ -270,6 +267,25 @@ __device__ __forceinline__ void store_cells(const StepArgs &a, int t, int j0, co
     }
 }
 
+// The general tail of an interior pair: rho / u where consumed (EMIT steps, solids), obstacle refill, stores.
+template <bool STRICT, bool EMIT, bool BB, bool PEER>
+__device__ __forceinline__ void finish_cells(const StepArgs &a, int t, int j0, unsigned code2, float (&g)[2][9], bool edge_w,
+                                             bool edge_e, float &vmax, int &vnan) {
+    float rho[2] = {0.f, 0.f}, ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const bool solid = (code2 >> c) & 1u;
+        if (EMIT || solid) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
+        if (solid) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
+            ux[c] = 0.0f; uy[c] = 0.0f;
+            if (BB) rho[c] = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
+        }
+    }
+    store_cells<EMIT, PEER>(a, t, j0, g, rho, ux, uy, edge_w, edge_e, vmax, vnan);
+}
+
 // Interior warp: one 64-cell segment of one interior column (see step_kernel).  `edge_w` / `edge_e`: the column is a slab
 // edge on the peer-memory path (warp-uniform) and its outgoing populations also go to the neighbour's halo column.
 template <bool STRICT, bool EMIT, bool BB, bool PEER>
@@ -334,7 +350,17 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
             f32x2 f2[9], g2[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) f2[k] = pack2(fin[0][k], fin[1][k]);
-            collide_strict_t<Lane2>(a.phys, f2, pack2(fmaxf(dx, dy.x), fmaxf(dx, dy.y)), g2);
+            // A non-finite relaxed moment (a run that is blowing up) takes the dense inverse AND its own copy of the tail:
+            // merging the two results in front of a shared tail cost six register moves on the hot path.
+            f32x2 ms2[9];
+            if (!collide_strict_front<Lane2>(a.phys, f2, pack2(fmaxf(dx, dy.x), fmaxf(dx, dy.y)), ms2)) {
+                Lane2::inverse_dense(ms2, g2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) unpack2(g2[k], g[0][k], g[1][k]);
+                finish_cells<STRICT, EMIT, BB, PEER>(a, t, j0, code2, g, edge_w, edge_e, vmax, vnan);
+                return;
+            }
+            collide_strict_back<Lane2>(ms2, g2);
 #pragma unroll
             for (int k = 0; k < 9; ++k) unpack2(g2[k], g[0][k], g[1][k]);
         } else {
@@ -348,18 +374,7 @@ __device__ __forceinline__ void interior_warp(const StepArgs &a, int il, int seg
         if (!EMIT && code2 == 0) {
             store_cells<EMIT, PEER>(a, t, j0, g, rho, ux, uy, edge_w, edge_e, vmax, vnan);
         } else {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const bool solid = (code2 >> c) & 1u;
-                if (EMIT || solid) macro_from_f<STRICT>(g[c], rho[c], ux[c], uy[c]);
-                if (solid) {  // obstacle refill, ref:452-455 (bounce-back mode: frozen at rest)
-                    ux[c] = 0.0f; uy[c] = 0.0f;
-                    if (BB) rho[c] = 1.0f;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) g[c][k] = __fmul_rn(kW[k], rho[c]);
-                }
-            }
-            store_cells<EMIT, PEER>(a, t, j0, g, rho, ux, uy, edge_w, edge_e, vmax, vnan);
+            finish_cells<STRICT, EMIT, BB, PEER>(a, t, j0, code2, g, edge_w, edge_e, vmax, vnan);
         }
     }
 }
@@ -405,9 +420,10 @@ __global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB)
     const int grp = vrow / (kRingGroup + 1), grp_r = vrow - grp * (kRingGroup + 1);
     const bool tb_row = grp_r == kRingGroup;
     const int col = grp * kRingGroup + grp_r;
-    // frame_count (ref:440): the step index and the ramp come from the host as kernel arguments, so nothing on the
-    // device reads this copy -- with early start a CTA of step n+1 may run before the last ring warp of step n.
-    if (a.bump_ctr && blockIdx.x == 0 && row == 0 && threadIdx.x == 0) *a.ctr_out = a.frame;
+    // frame_count (ref:440): the ramp value comes from the host as a kernel argument and nothing on the device reads a
+    // step counter -- with early start a CTA of step n+1 may run before the last ring warp of step n.  The diagnostic
+    // device copy of the counter is set once per lbm_run (set_counter_kernel), not by every CTA's prologue.
+
     float vmax = 0.0f;  // max |u|^2 over the cells written by this thread (EMIT only)
     int vnan = 0;
     // slab edge column (CTA-uniform; both false off the peer-memory slab path): wait for the neighbour's previous step
@@ -457,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, STRICT ? LBM_MINB_STRICT : LBM_MINB)
                 if (edge_here[1]) atomicAdd_system(a.peer_inbox[1], 1ULL);
             }
         }
-    } else if (col < a.il_count && seg < a.nseg && seg * kSegCells < a.ny) {
+    } else if (col < a.il_count && seg < a.nseg) {   // nseg = ceil(ny / 64): the segment starts inside the column
         // ------------------------------- interior warps --------------------------------------
         // slab edge columns (2 of thousands) take their own copy of the interior code with the neighbour stores compiled
         // in; every other column runs exactly the single-GPU code (sharing one copy cost 3.4 % of the step on ALL columns)
@@ -520,7 +536,8 @@ __global__ void halo_wait_kernel(const StepArgs a) {
     }
 }
 
-// Graph replay of a batch (lbm_run): the replayed step nodes carry no step index, the diagnostic counter is set behind them.
+// The diagnostic device copy of frame_count (lbm_step_count): set once behind the steps of an lbm_run call -- the step kernels
+// carry no step index (which is also what lets a batch be replayed as a CUDA graph).
 __global__ void set_counter_kernel(int *ctr, int value) { *ctr = value; }
 
 // Self test of Lane2's inline division / square root (lbm_selftest_arith): random operands from the guarded box
