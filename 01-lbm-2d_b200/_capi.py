@@ -70,6 +70,7 @@ EXPORTS = {
     "lbm_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lbm_device_view": (C.c_int, [C.c_void_p, C.POINTER(LbmDeviceView)]),
     "lbm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "lbm_graph_replay_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "lbm_selftest_arith": (C.c_int, [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
     "lbm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "lbm_host_free": (C.c_int, [C.c_void_p]),

@@ -190,6 +190,7 @@ struct LbmSolver {
     bool use_graph = true;
     int graph_min_steps = 8;
     std::map<long long, cudaGraphExec_t> graphs;
+    int64_t graph_replays = 0;
     bool pooled = false;                  // device memory through devpool (single-GPU handles)
     template <class T> cudaError_t dalloc(T **ptr, size_t bytes) { return devpool::alloc((void **)ptr, bytes, pooled); }
     unsigned long long *progress = nullptr;   // device counter, see step_kernel
@@ -1082,6 +1083,7 @@ int lbm_run(LbmHandle h, int steps) {
             hit = h->graphs.emplace(key, exec).first;
         }
         CUDA_TRY(cudaGraphLaunch(hit->second, h->stream));
+        h->graph_replays++;
         h->steps_done += steps;
         h->steps_total += steps;
         h->launches += steps;
@@ -1584,6 +1586,12 @@ int lbm_selftest_arith(int64_t pairs, uint64_t seed, int64_t mismatches[3]) {
 int lbm_launch_count(LbmHandle h, int64_t *launches) {
     if (!h || !launches) return fail(LBM_ERR_INVALID, "null argument");
     *launches = h->launches;
+    return LBM_OK;
+}
+
+int lbm_graph_replay_count(LbmHandle h, int64_t *replays) {
+    if (!h || !replays) return fail(LBM_ERR_INVALID, "null argument");
+    *replays = h->graph_replays;
     return LBM_OK;
 }
 

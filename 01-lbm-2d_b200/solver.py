@@ -323,6 +323,12 @@ class LBM2D_MRT_LES:
         _capi.check(self._lib.lbm_launch_count(self._h, C.byref(v)))
         return int(v.value)
 
+    def graph_replay_count(self) -> int:
+        """run_step() batches that were replayed as one CUDA graph (launch-bound grids)."""
+        v = C.c_int64()
+        _capi.check(self._lib.lbm_graph_replay_count(self._h, C.byref(v)))
+        return int(v.value)
+
     def device_view(self):
         v = _capi.LbmDeviceView()
         _capi.check(self._lib.lbm_device_view(self._h, C.byref(v)))

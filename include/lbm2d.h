@@ -208,6 +208,9 @@ int lbm_device_view(LbmHandle h, LbmDeviceView *out);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int lbm_launch_count(LbmHandle h, int64_t *launches);
+/* lbm_run() calls that were replayed as one CUDA graph (launch-bound grids, see lbm_run); their kernels are in
+ * lbm_launch_count() as well. */
+int lbm_graph_replay_count(LbmHandle h, int64_t *replays);
 
 /* Page-locked host memory for the large device -> host getters.  The reference hands out a FRESH (nx, ny, 9) numpy array
  * per export (ref:739-741; it is queued to the writer thread, io/lbm_writer.py:260-287), which as a pageable allocation
