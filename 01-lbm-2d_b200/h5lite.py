@@ -148,7 +148,7 @@ class Writer:
 
     def create_dataset(self, name, data, dtype=None):
         self._check_name(name)
-        a = np.ascontiguousarray(data, dtype)
+        a = np.asarray(data, dtype, order="C")   # (np.ascontiguousarray would turn a scalar into shape (1,))
         _dt_message(a.dtype)
         self.datasets[name] = ("contiguous", a.shape, a.dtype, self._write_raw(a) if a.nbytes else UNDEF, a.nbytes)
 
@@ -239,7 +239,7 @@ class Writer:
             raw = value.encode("utf-8") if isinstance(value, str) else value
             strings.append(raw)          # global heap object index = position + 1; the address is patched in by close()
             return name, raw, len(strings)
-        a = np.ascontiguousarray(value)
+        a = np.asarray(value, order="C")
         if a.dtype == np.bool_:
             a = a.astype(np.uint8)
         return _attribute_message(name, _dt_message(a.dtype), _space_message(a.shape), a.tobytes())

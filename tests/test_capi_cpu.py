@@ -73,6 +73,31 @@ def test_sass_shows_the_blackwell_paths_that_are_claimed():
         assert strict.count("FFMA2") == 19 and "FMUL2" not in strict, (name, strict.count("FFMA2"))
 
 
+def test_step_kernels_have_no_stack_frame_and_fit_their_occupancy_targets():
+    """Every warp of the step kernel pays for whatever its prologue sets up (a thread executes ~500 instructions per step, and
+    the kernel sits where issue rate and HBM meet): no stack frame on the plain steps -- the dense fallback for non-finite
+    moments is inline on registers -- and register counts that keep 9 (strict) / 10 (fast) CTAs of 128 threads per SM."""
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function\s+(\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            usage[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|LOCAL):(\d+)", line)}
+            name = None
+    def of(substr):
+        names = [n for n in usage if substr in n]
+        assert names, substr
+        return usage[names[0]]
+    for peer in ("Lb0E", "Lb1E"):   # single GPU / x-slab (peer-memory) instantiation
+        strict, fast = of("step_kernelILb1ELb0ELb0E" + peer), of("step_kernelILb0ELb0ELb0E" + peer)
+        assert strict["STACK"] == 0 and strict["LOCAL"] == 0 and strict["REG"] <= 56, strict      # 65536 / (9 * 128) = 56.9
+        assert fast["STACK"] == 0 and fast["LOCAL"] == 0 and fast["REG"] <= 48, fast              # 65536 / (10 * 128) = 51.2, pinned at 48
+        assert of("step_kernelILb1ELb1ELb0E" + peer)["STACK"] == 0                                  # strict EMIT step
+
+
 def test_struct_layout_matches_c(tmp_path):
     """Compile a tiny C program against the header and compare sizeof / offsetof with ctypes."""
     src = tmp_path / "layout.c"

@@ -153,3 +153,57 @@ def test_gzip_frames_use_the_standard_deflate_filter(tmp_path):
     offs, nbytes, fmask, addr = r.chunks(struct.unpack_from("<Q", lay, 3)[0], 5)[69]
     assert offs[0] == 69 and fmask == 0
     assert zlib.decompress(bytes(r.buf[addr:addr + nbytes])) == frames[69].tobytes()
+
+
+def test_random_case_files_round_trip():
+    """Property test: any mix of contiguous datasets (float / integer dtypes, ranks 0-4, empty ones), one or two appendable
+    datasets with or without deflate, numeric and string attributes comes back exactly, whatever order things were created in."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    import tempfile
+
+    dtypes = ["f4", "f8", "i4", "i8", "u1", "i2"]
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(st.data())
+    def run(data):
+        rng = np.random.default_rng(data.draw(st.integers(0, 2**31)))
+        n_plain = data.draw(st.integers(0, 11))
+        plain = {}
+        for i in range(n_plain):
+            shape = tuple(data.draw(st.lists(st.integers(0, 5), min_size=0, max_size=4)))
+            dt = data.draw(st.sampled_from(dtypes))
+            plain[f"d{i:02d}_{data.draw(st.sampled_from(['a', 'Z', '_', 'm']))}"] = (rng.standard_normal(shape) * 100).astype(dt)
+        n_app = data.draw(st.integers(0, 2))
+        apps = {}
+        for i in range(n_app):
+            fshape = tuple(data.draw(st.lists(st.integers(1, 4), min_size=1, max_size=3)))
+            n_frames = data.draw(st.sampled_from([0, 1, 2, 63, 64, 65, 130]))
+            apps[f"t{i}"] = ((rng.standard_normal((n_frames,) + fshape) * 3).astype("f4"), data.draw(st.sampled_from([None, 1, 6])))
+        attrs = {"s": data.draw(st.text(max_size=60)), "v": rng.standard_normal(data.draw(st.integers(1, 9))),
+                 "n": np.arange(data.draw(st.integers(1, 5)), dtype=np.int32)}
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "x.h5")
+            w = h5.Writer(path)
+            handles = {k: w.create_appendable(k, v[0].shape[1:], "f4", gzip=v[1]) for k, v in apps.items()}
+            names = list(plain)
+            for step in range(max([len(names)] + [len(v[0]) for v in apps.values()])):   # interleave creations and appends
+                if step < len(names):
+                    w.create_dataset(names[step], plain[names[step]])
+                for k, v in apps.items():
+                    if step < len(v[0]):
+                        handles[k].append(v[0][step])
+            for k, v in attrs.items():
+                w.set_attr(k, v)
+            w.close()
+            got = h5.read(path)
+            assert set(got) == set(plain) | set(apps) | {"attrs"}
+            for k, v in plain.items():
+                assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+            for k, v in apps.items():
+                assert got[k].shape == v[0].shape and np.array_equal(got[k], v[0]), k
+            assert got["attrs"]["s"] == attrs["s"] and np.array_equal(got["attrs"]["v"], attrs["v"])
+            assert got["attrs"]["n"].dtype == np.int32 and np.array_equal(got["attrs"]["n"], attrs["n"])
+            del got
+
+    run()
