@@ -133,6 +133,12 @@ def build_workload(name, n_gpus):
     return W.WORKLOADS[name]()
 
 
+def workload_label(name, nx, ny, world):
+    """`config.workload` of both arms (the reference arm times one GPU's share of it on the host)."""
+    return (f"{name} {nx}x{ny} (BASELINE {BASELINE_CONFIG.get(name, 'configs[2]')}" +
+            (" per GPU, its mask tiled along x" if world > 1 else "") + "), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]")
+
+
 def time_cpu_port(cfg, mask, budget_s, threads=None, steps=None):
     """The reference's three-pass step as restated in oracle/lbm_oracle.c, all host threads (cpu_baseline leg)."""
     from oracle import lbm_oracle_c
@@ -161,7 +167,7 @@ def run_reference(args):
     cfg, mask = build_workload(args.workload, 1)
     nx, ny = cfg["simulation"]["nx"], cfg["simulation"]["ny"]
     nx_full = nx
-    sample = f"{args.warmup}+{args.steps} full-grid steps of {nx}x{ny}"
+    sample = f"{args.warmup}+{args.steps} full-grid steps of {nx}x{ny}" + (f" (one GPU's share of the {args.gpus}-GPU workload)" if args.gpus > 1 else "")
     from oracle import lbm_oracle_c
 
     cores = os.cpu_count() or 1
@@ -191,7 +197,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload} {nx_full}x{ny} (BASELINE configs[2] per GPU), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
+            "workload": workload_label(args.workload, nx_full * max(1, args.gpus), ny, args.gpus),
             "grid": [nx, ny], "parallelism": f"host CPU, {cores} OpenMP threads (the reference's three-pass step, C port)",
             "sample": sample, "arith": "strict fp32 (reference evaluation order)",
         },
@@ -414,8 +420,7 @@ def run_ours(args):
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload} {nx}x{ny} (BASELINE {BASELINE_CONFIG.get(args.workload, 'configs[2]')}" +
-                        (" per GPU, its mask tiled along x" if world > 1 else "") + "), D2Q9 MRT-LES Cs=0.1, bc [0,2,1,2]",
+            "workload": workload_label(args.workload, nx, ny, world),
             "grid": [nx, ny], "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, 1 halo column / step, halo path: {halo_path}",
             "l2_policy": "working set 1.22 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
             "arith": args.arith, "kernel": args.kernel, "solid_fraction": float(mask.mean()),
